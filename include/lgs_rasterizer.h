@@ -1,0 +1,124 @@
+/*
+ * lgs_rasterizer.h -- C ABI of the B200-native LiDAR Gaussian rasterizer (liblgs_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of cqf7419/LiDAR-GS: each entry point replaces
+ * one static method of the reference's CudaRasterizer::Rasterizer
+ * (submodules/diff_lidargs_rasterization/cuda_rasterizer/rasterizer.h:24-122, "rasterizer.h"
+ * below).  Plain pointers and sizes only; every pointer is a DEVICE pointer unless stated;
+ * all work is enqueued on `stream` (a cudaStream_t passed as void*).  The library holds no
+ * state between calls except a small per-process pinned staging word.
+ *
+ * Error behaviour: functions returning int give >= 0 on success and a negative LGS_E* code on
+ * failure; lgs_last_error() returns a static message for the calling thread.  CUDA launch
+ * errors are reported (the reference only printf()s them, forward.cu:683-686).
+ */
+#ifndef LGS_RASTERIZER_H_
+#define LGS_RASTERIZER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGS_NUM_CHANNELS 2 /* reference config.h:15 */
+#define LGS_TILE_X 16      /* reference config.h:16 */
+#define LGS_TILE_Y 1       /* reference config.h:17 */
+
+#define LGS_EINVAL (-1)  /* bad argument (e.g. colors_precomp == NULL, rasterizer_impl.cu:249-252) */
+#define LGS_ECUDA (-2)   /* CUDA runtime error, see lgs_last_error() */
+#define LGS_ENOMEM (-3)  /* an allocator callback returned NULL */
+
+/*
+ * Scratch allocator callback: the C form of the reference's std::function<char*(size_t)>
+ * (rasterizer.h:32-34).  Called at most once per buffer per lgs_forward(); the returned device
+ * pointer (>= 256-byte aligned) must stay valid until the matching lgs_backward() has run.
+ */
+typedef char *(*lgs_alloc_fn)(size_t bytes, void *user);
+
+/*
+ * Forward render.  Replaces Rasterizer::forward (rasterizer.h:31-61; rasterizer_impl.cu:202-358).
+ * Same argument meaning and order; additions: the three `*_user` cookies for the C callbacks and
+ * `stream`.  D, M, shs, projmatrix, cam_pos, prefiltered are accepted for signature parity and
+ * ignored exactly as the reference's LiDAR path ignores them.  scales/rotations may be NULL iff
+ * cov3D_precomp is given.  radii (int[P]) is required; radii_xy (int[2P]) may be NULL.
+ * Outputs: out_color[2,H,W], out_depth[H,W], out_occ[H,W] (fully written, no pre-zeroing needed).
+ * Returns num_rendered = sum over Gaussians of 16x1 tiles touched (the reference's R), or < 0.
+ */
+int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user,
+                lgs_alloc_fn binning_buffer, void *binning_user,
+                lgs_alloc_fn image_buffer, void *image_user,
+                int P, int D, int M,
+                const float *background, int width, int height,
+                const float *means3D, const float *shs, const float *colors_precomp,
+                const float *opacities, const float *scales, float scale_modifier,
+                const float *rotations, const float *cov3D_precomp,
+                const float *viewmatrix, const float *projmatrix, const float *cam_pos,
+                const float *beam_inclinations, int prefiltered, int far, int near,
+                float *out_color, float *out_depth, float *out_occ,
+                int *radii, int *radii_xy, int debug, void *stream);
+
+/*
+ * Backward.  Replaces Rasterizer::backward (rasterizer.h:86-122; rasterizer_impl.cu:431-549).
+ * geom/binning/image buffers are the ones lgs_forward() filled.  The reference's five
+ * intermediate gradient arrays (dL_dconic, dL_ddepths, dL_dsphere_means3D, dL_dbasis_u1/u2 --
+ * rasterize_points.cu:163-175) are replaced by ONE packed scratch `grad_scratch` of
+ * lgs_backward_scratch_bytes(P) bytes that the library zeroes itself.  Every output is fully
+ * written (no pre-zeroing): dL_dmean2D[P,4], dL_dopacity[P], dL_dcolor[P,2], dL_dmean3D[P,3],
+ * dL_dcov3D[P,6] (may be NULL), dL_dscale[P,3] and dL_drot[P,4] (NULL iff cov3D_precomp given).
+ * dL_dsh is accepted and untouched (M == 0 on this path).
+ */
+int lgs_backward(int P, int D, int M, int R,
+                 const float *background, int width, int height,
+                 const float *means3D, const float *shs, const float *colors_precomp,
+                 const float *scales, float scale_modifier, const float *rotations,
+                 const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
+                 const float *campos, const float *beam_inclinations,
+                 float tan_fovx, float tan_fovy, const int *radii,
+                 char *geom_buffer, char *binning_buffer, char *image_buffer,
+                 const float *dL_dpix, const float *dL_dout_depth, const float *dL_dout_occ,
+                 float *grad_scratch,
+                 float *dL_dmean2D, float *dL_dopacity, float *dL_dcolor, float *dL_dmean3D,
+                 float *dL_dcov3D, float *dL_dsh, float *dL_dscale, float *dL_drot,
+                 int debug, void *stream);
+
+size_t lgs_backward_scratch_bytes(int P);
+
+/*
+ * Anchor pre-filter.  Replaces Rasterizer::visible_filter (rasterizer.h:64-82;
+ * rasterizer_impl.cu:362-426 -> forward.cu:389-497): writes radii[P] (0 = culled); radii_xy may be
+ * NULL.  No scratch is needed (the reference allocates a full GeometryState it never reads).
+ */
+int lgs_visible_filter(int P, int M, int width, int height,
+                       const float *means3D, const float *scales, float scale_modifier,
+                       const float *rotations, const float *cov3D_precomp,
+                       const float *viewmatrix, const float *projmatrix, const float *cam_pos,
+                       const float *beam_inclinations, float tan_fovx, float tan_fovy,
+                       int prefiltered, int far, int near, int *radii, int *radii_xy,
+                       int debug, void *stream);
+
+/*
+ * Replaces Rasterizer::markVisible (rasterizer.h:24-29; rasterizer_impl.cu:142-154):
+ * present[i] = (view-space z of point i > 0.2).  `present` is a byte per point (bool).
+ */
+int lgs_mark_visible(int P, const float *means3D, const float *viewmatrix,
+                     const float *projmatrix, unsigned char *present, void *stream);
+
+/* ---- knobs and introspection (no reference counterpart) -------------------------------- */
+
+/* Rows of 16x1 tiles that share one depth-binned list (1, 2, 4, 8 or 16; 0 = auto). */
+int lgs_set_rows_per_bin(int rows);
+/* 1 = sort every list completely in forward (tests); 0 = sort only what compositing consumes. */
+int lgs_set_sort_all(int on);
+/* Number of (Gaussian, bin) instances materialised by the last lgs_forward() on this thread. */
+long long lgs_last_num_instances(void);
+/* Kernels launched by this library since process start (bench.py's gpu_launches). */
+long long lgs_launch_count(void);
+const char *lgs_last_error(void);
+const char *lgs_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGS_RASTERIZER_H_ */

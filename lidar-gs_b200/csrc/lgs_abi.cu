@@ -1,0 +1,217 @@
+// lgs_abi.cu -- the extern "C" boundary declared in include/lgs_rasterizer.h: argument checks, scratch
+// carving, kernel sequencing on the caller's stream.  Mirrors the orchestration role of the
+// reference's CudaRasterizer::Rasterizer (R3 rasterizer_impl.cu:142-154, :202-358, :362-426,
+// :431-549) without its seven cudaDeviceSynchronize() calls: the only host wait left is the one
+// the interface itself demands (the scratch callback needs the instance count).
+#include "../../include/lgs_rasterizer.h"
+#include "lgs_kernels.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local FrameTotals *g_pinned = nullptr;
+thread_local long long g_last_instances = 0;
+std::atomic<int> g_rows_per_bin{0};
+std::atomic<int> g_sort_all{0};
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char *what, cudaError_t e = cudaSuccess)
+{
+	if (e != cudaSuccess) snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+	else snprintf(g_err, sizeof g_err, "%s", what);
+	return code;
+}
+
+#define CK(call)                                                          \
+	do {                                                              \
+		cudaError_t e_ = (call);                                  \
+		if (e_ != cudaSuccess) return fail(LGS_ECUDA, #call, e_); \
+	} while (0)
+
+int pick_rows_per_bin(int H)
+{
+	int rb = g_rows_per_bin.load();
+	if (rb != 1 && rb != 2 && rb != 4 && rb != 8 && rb != 16) rb = 8;
+	while (rb > 1 && rb > H) rb >>= 1;
+	return rb;
+}
+
+FrameGeom make_geom(int P, int W, int H)
+{
+	FrameGeom g;
+	g.P = P; g.W = W; g.H = H;
+	g.gx = (W + LGS_TILE_X_ - 1) / LGS_TILE_X_;
+	g.RB = pick_rows_per_bin(H);
+	g.nrg = (H + g.RB - 1) / g.RB;
+	g.nbins = g.gx * g.nrg;
+	return g;
+}
+
+} // namespace
+
+extern "C" {
+
+int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn binning_buffer, void *binning_user,
+		lgs_alloc_fn image_buffer, void *image_user, int P, int D, int M, const float *background, int width,
+		int height, const float *means3D, const float *shs, const float *colors_precomp, const float *opacities,
+		const float *scales, float scale_modifier, const float *rotations, const float *cov3D_precomp,
+		const float *viewmatrix, const float *projmatrix, const float *cam_pos, const float *beam_inclinations,
+		int prefiltered, int far, int near, float *out_color, float *out_depth, float *out_occ, int *radii,
+		int *radii_xy, int debug, void *stream)
+{
+	(void)D; (void)M; (void)shs; (void)projmatrix; (void)cam_pos; (void)prefiltered;
+	cudaStream_t st = (cudaStream_t)stream;
+	g_last_instances = 0;
+	if (P < 0 || width <= 0 || height <= 0) return fail(LGS_EINVAL, "lgs_forward: bad P / width / height");
+	if (width > 16 * 65535 || height > 65535) return fail(LGS_EINVAL, "lgs_forward: image too large for the packed rect");
+	if (!out_color || !out_depth || !out_occ) return fail(LGS_EINVAL, "lgs_forward: null output image");
+	const size_t HW = (size_t)width * height;
+	if (P == 0) { // rasterize_points.cu:87: zero images, R = 0
+		CK(cudaMemsetAsync(out_color, 0, HW * LGS_NUM_CHANNELS * 4, st));
+		CK(cudaMemsetAsync(out_depth, 0, HW * 4, st));
+		CK(cudaMemsetAsync(out_occ, 0, HW * 4, st));
+		return 0;
+	}
+	if (!colors_precomp) // rasterizer_impl.cu:249-252
+		return fail(LGS_EINVAL, "For non-RGB, provide precomputed Gaussian colors!");
+	if (!means3D || !opacities || !viewmatrix || !beam_inclinations || !background || !radii)
+		return fail(LGS_EINVAL, "lgs_forward: null input");
+	if (!cov3D_precomp && (!scales || !rotations)) return fail(LGS_EINVAL, "lgs_forward: need scales+rotations or cov3D_precomp");
+	if (far <= near) return fail(LGS_EINVAL, "lgs_forward: far <= near");
+	if (height < 2) return fail(LGS_EINVAL, "lgs_forward: beam table needs >= 2 rows");
+
+	FrameGeom g = make_geom(P, width, height);
+	GeomPtrs gsz = lgs_carve_geom(nullptr, g);
+	char *gb = geometry_buffer(gsz.bytes, geometry_user);
+	ImagePtrs isz = lgs_carve_image(nullptr, g);
+	char *ib = image_buffer(isz.bytes, image_user);
+	if (!gb || !ib) return fail(LGS_ENOMEM, "lgs_forward: scratch callback returned NULL");
+	GeomPtrs gp = lgs_carve_geom(gb, g);
+	ImagePtrs ip = lgs_carve_image(ib, g);
+
+	if (!g_pinned) CK(cudaMallocHost((void **)&g_pinned, sizeof(FrameTotals)));
+
+	CK(cudaMemsetAsync(gp.cnt, 0, (size_t)g.nbins * LGS_NB * 4, st));
+	CK(cudaMemsetAsync(gp.totals, 0, sizeof(FrameTotals), st));
+	lgs_launch_project(g, means3D, scales, scale_modifier, rotations, cov3D_precomp, opacities, colors_precomp,
+			   viewmatrix, beam_inclinations, far, near, gp, radii, radii_xy, st);
+	lgs_launch_scan(g, gp, st);
+	g_launches += 3;
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(g_pinned, gp.totals, sizeof(FrameTotals), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	const unsigned N = g_pinned->num_instances;
+	const unsigned long long R = g_pinned->num_rendered;
+	g_last_instances = N;
+	if (R > 0x7fffffffULL) return fail(LGS_EINVAL, "lgs_forward: num_rendered overflows int");
+
+	char *bb = binning_buffer((size_t)(N ? N : 1) * sizeof(uint4), binning_user);
+	if (!bb) return fail(LGS_ENOMEM, "lgs_forward: binning callback returned NULL");
+	uint4 *entries = (uint4 *)bb;
+	if (N) {
+		lgs_launch_scatter(g, gp, entries, N, st);
+		g_launches += 1;
+	}
+	lgs_launch_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_depth, out_occ,
+			      g_sort_all.load(), st);
+	g_launches += 1;
+	CK(cudaGetLastError());
+	if (debug) CK(cudaStreamSynchronize(st));
+	return (int)R;
+}
+
+size_t lgs_backward_scratch_bytes(int P) { return lgs_al((size_t)(P > 0 ? P : 1) * LGS_GRAD_STRIDE * sizeof(float)); }
+
+int lgs_backward(int P, int D, int M, int R, const float *background, int width, int height, const float *means3D,
+		 const float *shs, const float *colors_precomp, const float *scales, float scale_modifier,
+		 const float *rotations, const float *cov3D_precomp, const float *viewmatrix, const float *projmatrix,
+		 const float *campos, const float *beam_inclinations, float tan_fovx, float tan_fovy, const int *radii,
+		 char *geom_buffer, char *binning_buffer, char *image_buffer, const float *dL_dpix,
+		 const float *dL_dout_depth, const float *dL_dout_occ, float *grad_scratch, float *dL_dmean2D,
+		 float *dL_dopacity, float *dL_dcolor, float *dL_dmean3D, float *dL_dcov3D, float *dL_dsh,
+		 float *dL_dscale, float *dL_drot, int debug, void *stream)
+{
+	(void)D; (void)M; (void)R; (void)shs; (void)colors_precomp; (void)projmatrix; (void)campos;
+	(void)tan_fovx; (void)tan_fovy; (void)dL_dsh;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (P < 0 || width <= 0 || height <= 0) return fail(LGS_EINVAL, "lgs_backward: bad P / width / height");
+	if (P == 0) return 0;
+	if (!geom_buffer || !binning_buffer || !image_buffer || !grad_scratch)
+		return fail(LGS_EINVAL, "lgs_backward: null scratch buffer");
+	if (!dL_dpix || !dL_dout_depth || !dL_dout_occ) return fail(LGS_EINVAL, "lgs_backward: null upstream gradient");
+	if (!dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D) return fail(LGS_EINVAL, "lgs_backward: null output");
+	if (!means3D || !viewmatrix || !beam_inclinations || !background || !radii)
+		return fail(LGS_EINVAL, "lgs_backward: null input");
+	if (!cov3D_precomp && (!scales || !rotations)) return fail(LGS_EINVAL, "lgs_backward: need scales+rotations or cov3D_precomp");
+
+	FrameGeom g = make_geom(P, width, height);
+	GeomPtrs gp = lgs_carve_geom(geom_buffer, g);
+	ImagePtrs ip = lgs_carve_image(image_buffer, g);
+	CK(cudaMemsetAsync(grad_scratch, 0, (size_t)P * LGS_GRAD_STRIDE * sizeof(float), st));
+	lgs_launch_render_bwd(g, gp, ip, (const uint4 *)binning_buffer, background, beam_inclinations, dL_dpix,
+			      dL_dout_depth, dL_dout_occ, grad_scratch, st);
+	lgs_launch_finalize_bwd(g, means3D, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, radii,
+				grad_scratch, dL_dmean2D, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot,
+				st);
+	g_launches += 2;
+	CK(cudaGetLastError());
+	if (debug) CK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+int lgs_visible_filter(int P, int M, int width, int height, const float *means3D, const float *scales,
+		       float scale_modifier, const float *rotations, const float *cov3D_precomp, const float *viewmatrix,
+		       const float *projmatrix, const float *cam_pos, const float *beam_inclinations, float tan_fovx,
+		       float tan_fovy, int prefiltered, int far, int near, int *radii, int *radii_xy, int debug,
+		       void *stream)
+{
+	(void)M; (void)projmatrix; (void)cam_pos; (void)tan_fovx; (void)tan_fovy; (void)prefiltered;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (P < 0 || width <= 0 || height < 2) return fail(LGS_EINVAL, "lgs_visible_filter: bad P / width / height");
+	if (P == 0) return 0;
+	if (!means3D || !viewmatrix || !beam_inclinations || !radii) return fail(LGS_EINVAL, "lgs_visible_filter: null input");
+	if (!cov3D_precomp && (!scales || !rotations))
+		return fail(LGS_EINVAL, "lgs_visible_filter: need scales+rotations or cov3D_precomp");
+	lgs_launch_filter(P, means3D, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, width, height,
+			  beam_inclinations, far, near, radii, radii_xy, st);
+	g_launches += 1;
+	CK(cudaGetLastError());
+	if (debug) CK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+int lgs_mark_visible(int P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+		     unsigned char *present, void *stream)
+{
+	(void)projmatrix;
+	if (P < 0) return fail(LGS_EINVAL, "lgs_mark_visible: bad P");
+	if (P == 0) return 0;
+	if (!means3D || !viewmatrix || !present) return fail(LGS_EINVAL, "lgs_mark_visible: null input");
+	lgs_launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+	g_launches += 1;
+	CK(cudaGetLastError());
+	return 0;
+}
+
+int lgs_set_rows_per_bin(int rows)
+{
+	if (rows != 0 && rows != 1 && rows != 2 && rows != 4 && rows != 8 && rows != 16)
+		return fail(LGS_EINVAL, "lgs_set_rows_per_bin: rows must be 0, 1, 2, 4, 8 or 16");
+	g_rows_per_bin.store(rows);
+	return 0;
+}
+int lgs_set_sort_all(int on)
+{
+	g_sort_all.store(on ? 1 : 0);
+	return 0;
+}
+long long lgs_last_num_instances(void) { return g_last_instances; }
+long long lgs_launch_count(void) { return g_launches.load(); }
+const char *lgs_last_error(void) { return g_err; }
+const char *lgs_version(void) { return "lgs_b200 0.1 (sm_100a)"; }
+
+} // extern "C"

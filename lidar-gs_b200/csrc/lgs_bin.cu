@@ -1,0 +1,111 @@
+// lgs_bin.cu -- depth-bucketed binning: replaces the reference's inclusive scan + duplicateWithKeys +
+// global 64-bit radix sort + identifyTileRanges (R3 rasterizer_impl.cu:70-139, :288-331) with
+//   scan   : (bin, depth-bucket) counts -> offsets            (2 tiny launches)
+//   scatter: one 16-B entry per (Gaussian, bin) straight into its (bin, bucket) segment
+// Ordering inside a bucket is settled later, lazily, by the compositing kernel (lgs_render_fwd.cu);
+// buckets are monotone in depth so bucket-major order + in-bucket sort on (depth bits, idx) is the
+// order the reference's stable radix sort on tile|depth produces.
+#include "lgs_common.cuh"
+#include "lgs_kernels.h"
+
+namespace {
+
+__device__ __forceinline__ unsigned warp_excl_scan(unsigned v, unsigned &total)
+{
+	unsigned lane = threadIdx.x & 31, x = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+		if (lane >= (unsigned)o) x += y;
+	}
+	total = __shfl_sync(0xffffffffu, x, 31);
+	return x - v;
+}
+
+// one warp per bin: 64 bucket counts -> exclusive offsets inside the bin; counters reset to 0 so
+// the scatter can reuse them as cursors
+__global__ void __launch_bounds__(256)
+scan_bins_kernel(int nbins, uint32_t *__restrict__ cnt, uint32_t *__restrict__ loc, uint32_t *__restrict__ bintotal)
+{
+	int bin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	int lane = threadIdx.x & 31;
+	if (bin >= nbins) return;
+	uint32_t *c = cnt + (size_t)bin * LGS_NB;
+	unsigned c0 = c[lane], c1 = c[lane + 32], t0, t1;
+	unsigned s0 = warp_excl_scan(c0, t0);
+	unsigned s1 = warp_excl_scan(c1, t1) + t0;
+	loc[(size_t)bin * LGS_NB + lane] = s0;
+	loc[(size_t)bin * LGS_NB + lane + 32] = s1;
+	c[lane] = 0;
+	c[lane + 32] = 0;
+	if (lane == 0) bintotal[bin] = t0 + t1;
+}
+
+// single block: exclusive scan of the per-bin totals (in place: binbase[b] holds total on entry)
+__global__ void __launch_bounds__(1024)
+scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__restrict__ totals)
+{
+	__shared__ unsigned wsum[32];
+	__shared__ unsigned carry_s;
+	if (threadIdx.x == 0) carry_s = 0;
+	__syncthreads();
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	for (int base = 0; base < nbins; base += 1024) {
+		int i = base + threadIdx.x;
+		unsigned carry = carry_s; // stable: last written before the barrier that ended the previous pass
+		unsigned v = i < nbins ? binbase[i] : 0, tot;
+		unsigned ex = warp_excl_scan(v, tot);
+		if (lane == 0) wsum[w] = tot;
+		__syncthreads();
+		if (w == 0) {
+			unsigned t2, e2 = warp_excl_scan(wsum[lane], t2);
+			wsum[lane] = e2;
+			if (lane == 0) carry_s = carry + t2;
+		}
+		__syncthreads();
+		if (i < nbins) binbase[i] = carry + wsum[w] + ex;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		binbase[nbins] = carry_s;
+		totals->num_instances = carry_s;
+	}
+}
+
+// One thread per Gaussian (x-span x row-group-span instances each, ~3 on average).
+__global__ void __launch_bounds__(256)
+scatter_kernel(int P, int gx, int RB, const uint4 *__restrict__ aux, uint32_t *__restrict__ cursor,
+	       const uint32_t *__restrict__ loc, const uint32_t *__restrict__ binbase, uint4 *__restrict__ entries,
+	       unsigned capacity, FrameTotals *__restrict__ totals)
+{
+	int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >= P) return;
+	uint4 a = aux[idx];
+	int x0 = a.x & 0xffff, x1 = a.x >> 16, y0 = a.y & 0xffff, y1 = a.y >> 16;
+	if (x1 <= x0) return;
+	unsigned bucket = a.w;
+	uint4 e = make_uint4(a.z, (unsigned)idx, a.y, 0u);
+	int g0 = y0 / RB, g1 = (y1 - 1) / RB;
+	for (int g = g0; g <= g1; g++)
+		for (int x = x0; x < x1; x++) {
+			size_t bb = (size_t)(g * gx + x) * LGS_NB + bucket;
+			unsigned pos = binbase[g * gx + x] + loc[bb] + atomicAdd(&cursor[bb], 1u);
+			if (pos < capacity) entries[pos] = e;
+			else atomicAdd(&totals->overflow, 1u);
+		}
+}
+
+} // namespace
+
+void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, cudaStream_t st)
+{
+	int warps_per_block = 8;
+	scan_bins_kernel<<<(g.nbins + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(g.nbins, gp.cnt, gp.loc, gp.binbase);
+	scan_total_kernel<<<1, 1024, 0, st>>>(g.nbins, gp.binbase, gp.totals);
+}
+
+void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, unsigned capacity, cudaStream_t st)
+{
+	scatter_kernel<<<(g.P + 255) / 256, 256, 0, st>>>(g.P, g.gx, g.RB, gp.aux, gp.cnt, gp.loc, gp.binbase, entries,
+							  capacity, gp.totals);
+}

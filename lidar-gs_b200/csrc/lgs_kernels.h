@@ -1,0 +1,31 @@
+// lgs_kernels.h -- internal launch interface between the C-ABI layer (lgs_abi.cu) and the kernels.
+#pragma once
+#include "lgs_common.cuh"
+
+#define LGS_TILE_X_ 16
+#define LGS_TILE_Y_ 1
+
+void lgs_launch_project(const FrameGeom &g, const float *means3D, const float *scales, float mod,
+			const float *rotations, const float *cov3D_precomp, const float *opacities,
+			const float *colors, const float *view, const float *beams, int far_, int near_,
+			const GeomPtrs &gp, int *radii, int *radii_xy, cudaStream_t st);
+void lgs_launch_filter(int P, const float *means3D, const float *scales, float mod, const float *rotations,
+		       const float *cov3D_precomp, const float *view, int W, int H, const float *beams, int far_,
+		       int near_, int *radii, int *radii_xy, cudaStream_t st);
+void lgs_launch_mark_visible(int P, const float *means3D, const float *view, unsigned char *present, cudaStream_t st);
+
+// bucket counts -> per-bin exclusive offsets (loc), bin bases (binbase), totals->num_instances; cnt reset to 0
+void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, cudaStream_t st);
+// (Gaussian, bin) instances -> entries[], bin-major / bucket-minor, unordered inside a bucket
+void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, unsigned capacity, cudaStream_t st);
+
+void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries,
+			   const float *bg, const float *beams, float *out_color, float *out_depth, float *out_occ,
+			   int sort_all, cudaStream_t st);
+void lgs_launch_render_bwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, const uint4 *entries,
+			   const float *bg, const float *beams, const float *dL_dpix, const float *dL_ddepth,
+			   const float *dL_docc, float *grad, cudaStream_t st);
+void lgs_launch_finalize_bwd(const FrameGeom &g, const float *means3D, const float *scales, float mod,
+			     const float *rotations, const float *cov3D_precomp, const float *view, const int *radii,
+			     const float *grad, float *dL_dmean2D, float *dL_dopacity, float *dL_dcolor,
+			     float *dL_dmean3D, float *dL_dcov3D, float *dL_dscale, float *dL_drot, cudaStream_t st);

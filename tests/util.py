@@ -1,0 +1,92 @@
+"""Shared helpers for the test-suite: golden loading, error metrics, running the C ABI on a scene."""
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_golden(path):
+    g = np.load(path)
+    sc = {k[3:]: g[k] for k in g.files if k.startswith("in_")}
+    for k in ("far", "near", "H", "W"):
+        sc[k] = int(sc[k])
+    for k in ("scale_modifier", "tanfovx", "tanfovy"):
+        sc[k] = float(sc[k])
+    sc["P"] = int(sc["means3D"].shape[0])
+    return dict(name=os.path.basename(path)[:-4], sc=sc, g=g)
+
+
+def rel_norm(a, b):
+    """||a - b||_inf / ||b||_inf  (the backward gate of SURVEY.md §8d)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)) if a.size else 0.0
+
+
+def rel_elem(a, b, floor=1e-6):
+    """max_i |a_i - b_i| / max(|b_i|, floor)  (the forward gate of SURVEY.md §8d), plus outlier count."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    if a.size == 0:
+        return 0.0, 0
+    e = np.abs(a - b) / np.maximum(np.abs(b), floor)
+    return float(e.max()), int((e > 1e-4).sum())
+
+
+def to_torch(sc, dev):
+    import torch
+    return {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
+
+
+def run_abi(sc, dev="cuda:0", rows_per_bin=0, sort_all=False, backward=True, cov3D_precomp=None):
+    """forward (+ backward) through the C ABI of liblgs_b200.so; returns numpy results + the Frame."""
+    import torch
+    from lgs_b200 import capi
+    L = capi.load()
+    L.lgs_set_rows_per_bin(int(rows_per_bin))
+    L.lgs_set_sort_all(int(bool(sort_all)))
+    d = to_torch(sc, dev)
+    covp = None
+    if cov3D_precomp is not None:
+        covp = torch.from_numpy(np.ascontiguousarray(cov3D_precomp, dtype=np.float32)).to(dev)
+    fr = capi.Frame(torch.device(dev))
+    out = fr.forward(d["bg"], d["means3D"], d["colors"], d["opacities"], None if covp is not None else d["scales"],
+                     None if covp is not None else d["rotations"], d["viewmatrix"], d["beams"], sc["H"], sc["W"],
+                     sc["far"], sc["near"], sc.get("scale_modifier", 1.0), cov3D_precomp=covp)
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    res["num_rendered"] = fr.num_rendered
+    res["num_instances"] = fr.num_instances
+    if backward:
+        gr = fr.backward(d["g_color"], d["g_depth"], d["g_occ"])
+        torch.cuda.synchronize()
+        res["grads"] = {k: v.cpu().numpy() for k, v in gr.items() if v is not None and k != "scratch"}
+    L.lgs_set_rows_per_bin(0)
+    L.lgs_set_sort_all(0)
+    return res, fr
+
+
+def decode_frame(fr, sc, rows_per_bin):
+    """White-box view of our scratch buffers (layout: lidar-gs_b200/csrc/lgs_common.cuh)."""
+    P, H, W = sc["P"], sc["H"], sc["W"]
+    gx = (W + 15) // 16
+    RB = rows_per_bin
+    while RB > 1 and RB > H:
+        RB >>= 1
+    nrg = (H + RB - 1) // RB
+    nbins = gx * nrg
+    al = lambda x: (x + 255) & ~255
+    gb = fr.geom.cpu().numpy()
+    o = 0
+    rec = gb[o:o + 64 * P].view(np.float32).reshape(P, 16).copy(); o = al(o + 64 * P)
+    aux = gb[o:o + 16 * P].view(np.uint32).reshape(P, 4).copy(); o = al(o + 16 * P)
+    cnt = gb[o:o + nbins * 64 * 4].view(np.uint32).reshape(nbins, 64).copy(); o = al(o + nbins * 64 * 4)
+    loc = gb[o:o + nbins * 64 * 4].view(np.uint32).reshape(nbins, 64).copy(); o = al(o + nbins * 64 * 4)
+    binbase = gb[o:o + (nbins + 1) * 4].view(np.uint32).copy(); o = al(o + (nbins + 1) * 4)
+    ib = fr.image.cpu().numpy()
+    o = 0
+    final_T = ib[o:o + 4 * H * W].view(np.float32).reshape(H, W).copy(); o = al(o + 4 * H * W)
+    n_contrib = ib[o:o + 4 * H * W].view(np.uint32).reshape(H, W).copy(); o = al(o + 4 * H * W)
+    sorted_end = ib[o:o + 4 * nbins].view(np.uint32).copy()
+    N = int(binbase[-1])
+    ent = fr.binning.cpu().numpy()[:16 * N].view(np.uint32).reshape(N, 4).copy()
+    return dict(rec=rec, aux=aux, cnt=cnt, loc=loc, binbase=binbase, final_T=final_T, n_contrib=n_contrib,
+                sorted_end=sorted_end, entries=ent, RB=RB, gx=gx, nbins=nbins)
