@@ -113,6 +113,24 @@ int lgs_set_rows_per_bin(int rows);
 int lgs_set_sort_all(int on);
 /* Number of (Gaussian, bin) instances materialised by the last lgs_forward() on this thread. */
 long long lgs_last_num_instances(void);
+/*
+ * Per-stage device timing with CUDA events recorded on the caller's stream around each stage
+ * (bench.py's roofline leg).  Enable, run any number of calls on this thread, then collect:
+ * ms_per_stage / launches_per_stage are arrays of LGS_NUM_STAGES entries (sums since enable).
+ */
+enum {
+	LGS_STAGE_CLEAR = 0,    /* memsets: bucket counters, gradient accumulator */
+	LGS_STAGE_PROJECT = 1,  /* per-Gaussian projection + record packing + bucket counting */
+	LGS_STAGE_SCAN = 2,     /* bucket counts -> offsets (2 launches) */
+	LGS_STAGE_SCATTER = 3,  /* (Gaussian, bin) instances -> depth-bucketed lists */
+	LGS_STAGE_RENDER_FWD = 4, /* lazy per-bin sort + front-to-back compositing */
+	LGS_STAGE_RENDER_BWD = 5, /* back-to-front gradient pass */
+	LGS_STAGE_FINALIZE_BWD = 6, /* per-Gaussian chain rule, writes all API grads */
+	LGS_STAGE_FILTER = 7,   /* anchor visibility pre-filter */
+	LGS_NUM_STAGES = 8
+};
+int lgs_timing_enable(int on);
+int lgs_timing_collect(double *ms_per_stage, long long *launches_per_stage);
 /* Kernels launched by this library since process start (bench.py's gpu_launches). */
 long long lgs_launch_count(void);
 const char *lgs_last_error(void);

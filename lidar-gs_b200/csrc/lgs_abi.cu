@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 namespace {
 
@@ -18,6 +19,33 @@ thread_local long long g_last_instances = 0;
 std::atomic<int> g_rows_per_bin{0};
 std::atomic<int> g_sort_all{0};
 std::atomic<long long> g_launches{0};
+
+// ---- optional per-stage CUDA-event timing (bench.py's roofline leg) ---------------------------
+struct StageTimer {
+	bool on = false;
+	std::vector<cudaEvent_t> ev; // pairs (begin, end)
+	std::vector<int> stage;
+	size_t used = 0;
+	void begin(int id, cudaStream_t st)
+	{
+		if (!on) return;
+		if (used + 2 > ev.size()) {
+			size_t n = ev.size() ? ev.size() * 2 : 1024;
+			size_t old = ev.size();
+			ev.resize(n);
+			for (size_t i = old; i < n; i++) cudaEventCreate(&ev[i]);
+		}
+		stage.push_back(id);
+		cudaEventRecord(ev[used], st);
+	}
+	void end(cudaStream_t st)
+	{
+		if (!on) return;
+		cudaEventRecord(ev[used + 1], st);
+		used += 2;
+	}
+};
+thread_local StageTimer g_timer;
 
 int fail(int code, const char *what, cudaError_t e = cudaSuccess)
 {
@@ -95,11 +123,17 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn 
 
 	if (!g_pinned) CK(cudaMallocHost((void **)&g_pinned, sizeof(FrameTotals)));
 
+	g_timer.begin(LGS_STAGE_CLEAR, st);
 	CK(cudaMemsetAsync(gp.cnt, 0, (size_t)g.nbins * LGS_NB * 4, st));
 	CK(cudaMemsetAsync(gp.totals, 0, sizeof(FrameTotals), st));
+	g_timer.end(st);
+	g_timer.begin(LGS_STAGE_PROJECT, st);
 	lgs_launch_project(g, means3D, scales, scale_modifier, rotations, cov3D_precomp, opacities, colors_precomp,
 			   viewmatrix, beam_inclinations, far, near, gp, radii, radii_xy, st);
+	g_timer.end(st);
+	g_timer.begin(LGS_STAGE_SCAN, st);
 	lgs_launch_scan(g, gp, st);
+	g_timer.end(st);
 	g_launches += 3;
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(g_pinned, gp.totals, sizeof(FrameTotals), cudaMemcpyDeviceToHost, st));
@@ -113,11 +147,15 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn 
 	if (!bb) return fail(LGS_ENOMEM, "lgs_forward: binning callback returned NULL");
 	uint4 *entries = (uint4 *)bb;
 	if (N) {
+		g_timer.begin(LGS_STAGE_SCATTER, st);
 		lgs_launch_scatter(g, gp, entries, N, st);
+		g_timer.end(st);
 		g_launches += 1;
 	}
+	g_timer.begin(LGS_STAGE_RENDER_FWD, st);
 	lgs_launch_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_depth, out_occ,
 			      g_sort_all.load(), st);
+	g_timer.end(st);
 	g_launches += 1;
 	CK(cudaGetLastError());
 	if (debug) CK(cudaStreamSynchronize(st));
@@ -151,12 +189,18 @@ int lgs_backward(int P, int D, int M, int R, const float *background, int width,
 	FrameGeom g = make_geom(P, width, height);
 	GeomPtrs gp = lgs_carve_geom(geom_buffer, g);
 	ImagePtrs ip = lgs_carve_image(image_buffer, g);
+	g_timer.begin(LGS_STAGE_CLEAR, st);
 	CK(cudaMemsetAsync(grad_scratch, 0, (size_t)P * LGS_GRAD_STRIDE * sizeof(float), st));
+	g_timer.end(st);
+	g_timer.begin(LGS_STAGE_RENDER_BWD, st);
 	lgs_launch_render_bwd(g, gp, ip, (const uint4 *)binning_buffer, background, beam_inclinations, dL_dpix,
 			      dL_dout_depth, dL_dout_occ, grad_scratch, st);
+	g_timer.end(st);
+	g_timer.begin(LGS_STAGE_FINALIZE_BWD, st);
 	lgs_launch_finalize_bwd(g, means3D, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, radii,
 				grad_scratch, dL_dmean2D, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot,
 				st);
+	g_timer.end(st);
 	g_launches += 2;
 	CK(cudaGetLastError());
 	if (debug) CK(cudaStreamSynchronize(st));
@@ -176,8 +220,10 @@ int lgs_visible_filter(int P, int M, int width, int height, const float *means3D
 	if (!means3D || !viewmatrix || !beam_inclinations || !radii) return fail(LGS_EINVAL, "lgs_visible_filter: null input");
 	if (!cov3D_precomp && (!scales || !rotations))
 		return fail(LGS_EINVAL, "lgs_visible_filter: need scales+rotations or cov3D_precomp");
+	g_timer.begin(LGS_STAGE_FILTER, st);
 	lgs_launch_filter(P, means3D, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, width, height,
 			  beam_inclinations, far, near, radii, radii_xy, st);
+	g_timer.end(st);
 	g_launches += 1;
 	CK(cudaGetLastError());
 	if (debug) CK(cudaStreamSynchronize(st));
@@ -207,6 +253,30 @@ int lgs_set_rows_per_bin(int rows)
 int lgs_set_sort_all(int on)
 {
 	g_sort_all.store(on ? 1 : 0);
+	return 0;
+}
+int lgs_timing_enable(int on)
+{
+	g_timer.on = on != 0;
+	g_timer.used = 0;
+	g_timer.stage.clear();
+	return 0;
+}
+int lgs_timing_collect(double *ms_per_stage, long long *launches_per_stage)
+{
+	for (int i = 0; i < LGS_NUM_STAGES; i++) {
+		ms_per_stage[i] = 0.0;
+		launches_per_stage[i] = 0;
+	}
+	if (g_timer.used) CK(cudaEventSynchronize(g_timer.ev[g_timer.used - 1]));
+	for (size_t k = 0; k < g_timer.used / 2; k++) {
+		float ms = 0.f;
+		CK(cudaEventElapsedTime(&ms, g_timer.ev[2 * k], g_timer.ev[2 * k + 1]));
+		ms_per_stage[g_timer.stage[k]] += ms;
+		launches_per_stage[g_timer.stage[k]] += 1;
+	}
+	g_timer.used = 0;
+	g_timer.stage.clear();
 	return 0;
 }
 long long lgs_last_num_instances(void) { return g_last_instances; }

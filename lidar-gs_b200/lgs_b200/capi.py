@@ -13,7 +13,7 @@ ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 _lib = None
 
 SYMBOLS = ["lgs_forward", "lgs_backward", "lgs_backward_scratch_bytes", "lgs_visible_filter", "lgs_mark_visible",
-           "lgs_set_rows_per_bin", "lgs_set_sort_all", "lgs_last_num_instances", "lgs_launch_count",
+           "lgs_set_rows_per_bin", "lgs_set_sort_all", "lgs_timing_enable", "lgs_timing_collect", "lgs_last_num_instances", "lgs_launch_count",
            "lgs_last_error", "lgs_version"]
 
 
@@ -39,6 +39,8 @@ def load():
     L.lgs_mark_visible.argtypes = [i, vp, vp, vp, vp, vp]
     L.lgs_set_rows_per_bin.argtypes = [i]
     L.lgs_set_sort_all.argtypes = [i]
+    L.lgs_timing_enable.argtypes = [i]
+    L.lgs_timing_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.lgs_last_num_instances.restype = C.c_longlong
     L.lgs_launch_count.restype = C.c_longlong
     L.lgs_last_error.restype = C.c_char_p
@@ -144,3 +146,18 @@ def mark_visible(means3D, view, stream=None):
     st = torch.cuda.current_stream(means3D.device).cuda_stream if stream is None else stream
     _check(L.lgs_mark_visible(P, _ptr(means3D), _ptr(view), None, _ptr(out), C.c_void_p(st)))
     return out
+
+
+STAGES = ["clear", "project", "scan", "scatter", "render_fwd", "render_bwd", "finalize_bwd", "filter"]
+
+
+def timing_enable(on=True):
+    load().lgs_timing_enable(int(on))
+
+
+def timing_collect():
+    """-> {stage: (total_ms, launches)} since timing_enable(True)"""
+    ms = (C.c_double * len(STAGES))()
+    n = (C.c_longlong * len(STAGES))()
+    _check(load().lgs_timing_collect(ms, n))
+    return {s: (ms[k], n[k]) for k, s in enumerate(STAGES)}
