@@ -90,3 +90,56 @@ def decode_frame(fr, sc, rows_per_bin):
     ent = fr.binning.cpu().numpy()[:16 * N].view(np.uint32).reshape(N, 4).copy()
     return dict(rec=rec, aux=aux, cnt=cnt, loc=loc, binbase=binbase, final_T=final_T, n_contrib=n_contrib,
                 sorted_end=sorted_end, entries=ent, RB=RB, gx=gx, nbins=nbins)
+
+
+# ---- gates --------------------------------------------------------------------
+FWD_TOL = 1e-4   # forward images: |a - b| / max(|b|, floor)
+BWD_TOL = 1e-3   # gradients: ||a - b||_inf / ||b||_inf
+
+
+def assert_forward_close(res, ref, floor=1e-6, max_outlier_frac=0.0, what=""):
+    """res / ref: dicts with color, depth, occ.  Per-element relative gate of SURVEY.md §8d; a fraction of
+    outliers may be allowed when the checker is the CPU oracle (libm vs libdevice ulps)."""
+    for k in ("color", "depth", "occ"):
+        a, b = np.asarray(res[k]), np.asarray(ref[k])
+        assert a.shape == b.shape, (what, k, a.shape, b.shape)
+        assert np.isfinite(a).all(), (what, k, "non-finite output")
+        e, nout = rel_elem(a, b, floor)
+        assert rel_norm(a, b) <= FWD_TOL, (what, k, "norm-rel", rel_norm(a, b))
+        assert nout <= max_outlier_frac * a.size, (what, k, "elem-rel max", e, "outliers", nout, "of", a.size)
+
+
+def assert_grads_close(grads, ref, skip=(), tol=BWD_TOL, what=""):
+    for k, v in grads.items():
+        if k in skip or k not in ref:
+            continue
+        r = np.asarray(ref[k]).reshape(v.shape)
+        assert np.isfinite(v).all(), (what, k, "non-finite gradient")
+        assert rel_norm(v, r) <= tol, (what, k, rel_norm(v, r))
+
+
+def oracle_run(sc, cov3D_precomp=None, backward=True):
+    """The checker: CPU restatement of the reference (oracle/lgs_oracle.c)."""
+    import lgs_oracle as O
+    f = O.Forward(sc, cov3D_precomp=cov3D_precomp)
+    out = dict(color=f.color, depth=f.depth, occ=f.occ, radii=f.radii, num_rendered=f.num_rendered)
+    if backward:
+        out["grads"] = f.backward(sc["g_color"], sc["g_depth"], sc["g_occ"])
+    out["internals"] = f.internals()
+    f.close()
+    return out
+
+
+def cov3d_numpy(scales, rots, mod=1.0):
+    """Sigma = R S^2 R^T, upper triangle (6 floats), quaternion (r, x, y, z) used as given -- the layout
+    cov3D_precomp has in the reference (fwd.cu:216-253)."""
+    s = (np.asarray(scales, np.float64) * mod)
+    q = np.asarray(rots, np.float64)
+    r, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.empty((q.shape[0], 3, 3))
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - r * z); R[:, 0, 2] = 2 * (x * z + r * y)
+    R[:, 1, 0] = 2 * (x * y + r * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - r * x)
+    R[:, 2, 0] = 2 * (x * z - r * y); R[:, 2, 1] = 2 * (y * z + r * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    Sg = np.einsum("nij,nj,nkj->nik", R, s * s, R)
+    return np.ascontiguousarray(np.stack([Sg[:, 0, 0], Sg[:, 0, 1], Sg[:, 0, 2], Sg[:, 1, 1], Sg[:, 1, 2], Sg[:, 2, 2]], 1),
+                                dtype=np.float32)
