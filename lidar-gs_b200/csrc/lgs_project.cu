@@ -4,49 +4,13 @@
 // Restates R3 forward.cu:257-384 (preprocessCUDA) / :389-497 (filter_preprocessCUDA) with
 // computeCov3D :216-253, _proj_2basis :95-119, computeCov2D_lidar :146-169, find_closest_label
 // aux.h:41-63, getRect_lidar aux.h:80-92, and checkFrustum rasterizer_impl.cu:54-66.
-// Expressions keep the reference's association order (and its float/double promotions) so that
-// nvcc contracts them the same way: every value that feeds a threshold (radii, rect, conic, s,
-// u1, u2, depth) is meant to be bit-identical to the reference's.
+// Every value that feeds a threshold (radii, rect, conic, s, u1, u2, depth) is bit-identical to the
+// reference's: FMA contraction is pinned with _rn intrinsics in the order of the reference's sm_100a SASS,
+// float/double promotions are kept where its literals cause them.
 #include "lgs_common.cuh"
 #include "lgs_kernels.h"
 
 namespace {
-
-// column-major 3x3 with the same element expression order as glm::mat3 operator*
-struct M3 {
-	float m[3][3]; // m[c][r]
-};
-__device__ __forceinline__ M3 mul(const M3 &a, const M3 &b)
-{
-	M3 o;
-#pragma unroll
-	for (int c = 0; c < 3; c++)
-#pragma unroll
-		for (int r = 0; r < 3; r++)
-			o.m[c][r] = a.m[0][r] * b.m[c][0] + a.m[1][r] * b.m[c][1] + a.m[2][r] * b.m[c][2];
-	return o;
-}
-__device__ __forceinline__ M3 transpose(const M3 &a)
-{
-	M3 o;
-#pragma unroll
-	for (int c = 0; c < 3; c++)
-#pragma unroll
-		for (int r = 0; r < 3; r++)
-			o.m[c][r] = a.m[r][c];
-	return o;
-}
-
-__device__ __forceinline__ float3 unit3(float3 v)
-{ // fwd.cu:80-88
-	float length = sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
-	if (length > 0.0f) {
-		v.x /= length;
-		v.y /= length;
-		v.z /= length;
-	}
-	return v;
-}
 
 __device__ __forceinline__ int beam_lower_bound(const float *__restrict__ b, float a, int n)
 { // aux.h:41-63
@@ -81,13 +45,16 @@ __device__ __forceinline__ bool project_gaussian(int idx, const float *__restric
 {
 	const float pi = 3.14159265358979323846f;
 	const float Ray_Divergence_Angle = 0.002f;
-	float3 p_orig = {orig_points[3 * idx], orig_points[3 * idx + 1], orig_points[3 * idx + 2]};
-	float3 p_view = {
-		view[0] * p_orig.x + view[4] * p_orig.y + view[8] * p_orig.z + view[12],
-		view[1] * p_orig.x + view[5] * p_orig.y + view[9] * p_orig.z + view[13],
-		view[2] * p_orig.x + view[6] * p_orig.y + view[10] * p_orig.z + view[14],
+	// Every expression below that ptxas could contract into an FMA is written with explicit _rn intrinsics in
+	// the order the reference's sm_100a SASS uses (preprocessCUDA 0x410-0x1d90: a0*b0 + a1*b1 + a2*b2 is
+	// fma(a2, b2, fma(a0, b0, fl(a1*b1))) throughout), so the record is bit-identical to the reference's state.
+	const float px = orig_points[3 * idx], py = orig_points[3 * idx + 1], pz = orig_points[3 * idx + 2];
+	float3 p_view = { // aux.h:94-102 transformPoint4x3
+		__fadd_rn(lgs_dot3m(px, view[0], py, view[4], pz, view[8]), view[12]),
+		__fadd_rn(lgs_dot3m(px, view[1], py, view[5], pz, view[9]), view[13]),
+		__fadd_rn(lgs_dot3m(px, view[2], py, view[6], pz, view[10]), view[14]),
 	};
-	float dist = sqrt((p_view.x) * (p_view.x) + (p_view.y) * (p_view.y) + (p_view.z) * (p_view.z));
+	const float dist = __fsqrt_rn(lgs_dot_self(p_view.x, p_view.y, p_view.z));
 	if (dist >= far_ || dist <= near_) return false;
 
 	float cov3D[6];
@@ -95,60 +62,62 @@ __device__ __forceinline__ bool project_gaussian(int idx, const float *__restric
 #pragma unroll
 		for (int k = 0; k < 6; k++) cov3D[k] = cov3D_precomp[6 * idx + k];
 	} else {
-		M3 S = {{{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}};
-		S.m[0][0] = mod * scales[3 * idx + 0];
-		S.m[1][1] = mod * scales[3 * idx + 1];
-		S.m[2][2] = mod * scales[3 * idx + 2];
-		float r = rotations[4 * idx + 0], x = rotations[4 * idx + 1], y = rotations[4 * idx + 2], z = rotations[4 * idx + 3];
-		M3 R = {{{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
-			 {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
-			 {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}}};
-		M3 M = mul(S, R);
-		M3 Sigma = mul(transpose(M), M);
-		cov3D[0] = Sigma.m[0][0];
-		cov3D[1] = Sigma.m[0][1];
-		cov3D[2] = Sigma.m[0][2];
-		cov3D[3] = Sigma.m[1][1];
-		cov3D[4] = Sigma.m[1][2];
-		cov3D[5] = Sigma.m[2][2];
+		Cov3D cv3;
+		lgs_cov3d_from_scale_rot(scales[3 * idx + 0], scales[3 * idx + 1], scales[3 * idx + 2], mod, rotations[4 * idx + 0],
+					 rotations[4 * idx + 1], rotations[4 * idx + 2], rotations[4 * idx + 3], cv3);
+#pragma unroll
+		for (int k = 0; k < 6; k++) cov3D[k] = cv3.c[k];
 	}
 
 	// tangent basis at the Gaussian's direction (fwd.cu:95-119)
-	float3 dir = unit3(p_view);
-	float3 u1 = {dir.y, -dir.x, 0};
-	u1 = unit3(u1);
-	float3 u2 = {
-		dir.y * u1.z - dir.z * u1.y,
-		dir.z * u1.x - dir.x * u1.z,
-		dir.x * u1.y - dir.y * u1.x,
+	float3 dir = p_view;
+	if (dist > 0.0f) dir = {__fdiv_rn(p_view.x, dist), __fdiv_rn(p_view.y, dist), __fdiv_rn(p_view.z, dist)};
+	float3 u1 = {dir.y, -dir.x, 0.f};
+	{
+		const float len = __fsqrt_rn(__fmaf_rn(dir.y, dir.y, __fmul_rn(dir.x, dir.x)));
+		if (len > 0.0f) u1 = {__fdiv_rn(u1.x, len), __fdiv_rn(u1.y, len), __fdiv_rn(0.f, len)};
+	}
+	const float3 u2 = {
+		__fmaf_rn(u1.z, dir.y, -__fmul_rn(u1.y, dir.z)),
+		__fmaf_rn(u1.x, dir.z, -__fmul_rn(u1.z, dir.x)),
+		__fmaf_rn(u1.y, dir.x, -__fmul_rn(u1.x, dir.y)),
 	};
-	M3 Pm = {{{u1.x, u1.y, u1.z}, {u2.x, u2.y, u2.z}, {0, 0, 0}}};
-	// covariance on the tangent plane (fwd.cu:146-169)
-	M3 Wm = {{{view[0], view[4], view[8]}, {view[1], view[5], view[9]}, {view[2], view[6], view[10]}}};
-	M3 T = mul(Wm, Pm);
-	M3 Vrk = {{{cov3D[0], cov3D[1], cov3D[2]}, {cov3D[1], cov3D[3], cov3D[4]}, {cov3D[2], cov3D[4], cov3D[5]}}};
-	M3 cv = mul(mul(transpose(T), transpose(Vrk)), T);
-	cv.m[0][0] += 0.01f;
-	cv.m[1][1] += 0.01f;
-	float3 cov = {float(cv.m[0][0]), float(cv.m[0][1]), float(cv.m[1][1])};
-	cov.x = cov.x / (dist * dist);
-	cov.y = cov.y / (dist * dist);
-	cov.z = cov.z / (dist * dist);
-	float det = (cov.x * cov.z - cov.y * cov.y);
+	// covariance on the tangent plane (fwd.cu:146-169): T = W P, cov = T^T Vrk^T T (upper-left 2x2)
+	float T0[3], T1[3];
+#pragma unroll
+	for (int r = 0; r < 3; r++) {
+		T0[r] = lgs_dot3m(view[4 * r], u1.x, view[4 * r + 1], u1.y, view[4 * r + 2], u1.z);
+		T1[r] = lgs_dot3m(u2.x, view[4 * r], u2.y, view[4 * r + 1], u2.z, view[4 * r + 2]);
+	}
+	const float V[3][3] = {{cov3D[0], cov3D[1], cov3D[2]}, {cov3D[1], cov3D[3], cov3D[4]}, {cov3D[2], cov3D[4], cov3D[5]}};
+	float A0[3], A1[3]; // A[k][r] = sum_j T[r][j] Vrk[j][k]
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		A0[k] = lgs_dot3m(T0[0], V[0][k], T0[1], V[1][k], T0[2], V[2][k]);
+		A1[k] = lgs_dot3m(T1[0], V[0][k], T1[1], V[1][k], T1[2], V[2][k]);
+	}
+	const float c00 = __fadd_rn(lgs_dot3m(T0[0], A0[0], T0[1], A0[1], T0[2], A0[2]), 0.01f);
+	const float c01 = lgs_dot3m(T0[0], A1[0], T0[1], A1[1], T0[2], A1[2]);
+	const float c11 = __fadd_rn(lgs_dot3m(T1[0], A1[0], T1[1], A1[1], T1[2], A1[2]), 0.01f);
+	const float d2 = __fmul_rn(dist, dist);
+	float3 cov = {__fdiv_rn(c00, d2), __fdiv_rn(c01, d2), __fdiv_rn(c11, d2)};
+	const float det = __fmaf_rn(cov.z, cov.x, -__fmul_rn(cov.y, cov.y));
 	if (det == 0.0f) return false;
-	float det_inv = 1.f / det;
-	float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
-	float mid = 0.5f * (cov.x + cov.z);
-	// 1e-9 literals are double: max/sqrt/add run in fp64 (fwd.cu:328-330)
-	float lambda1 = mid + sqrt(max(1e-9, mid * mid - det));
-	float lambda2 = mid - sqrt(max(1e-9, mid * mid - det));
+	const float det_inv = __frcp_rn(det);
+	float3 conic = {__fmul_rn(det_inv, cov.z), __fmul_rn(det_inv, -cov.y), __fmul_rn(det_inv, cov.x)};
+	const float mid = __fmul_rn(__fadd_rn(cov.z, cov.x), 0.5f);
+	// 1e-9 literals are double: max/sqrt/add run in fp64 (fwd.cu:328-330); mid*mid - det is one float FMA
+	const double disc = sqrt(max(1e-9, (double)__fmaf_rn(mid, mid, -det)));
+	float lambda1 = (float)((double)mid + disc);
+	float lambda2 = (float)((double)mid - disc);
 	float my_radius = sqrt(max(1e-9, max(lambda1, lambda2)));
 
 	float beta = pi - atan2(p_view.y, p_view.x);
 	float p_c = beta / (2 * pi / W);
 	float alpha;
-	if (!FILTER) alpha = atan2(p_view.z, sqrt(p_view.x * p_view.x + p_view.y * p_view.y));
-	else alpha = atan2((double)p_view.z, sqrt(max(1e-9, p_view.x * p_view.x + p_view.y * p_view.y)));
+	const float h2 = __fmaf_rn(p_view.x, p_view.x, __fmul_rn(p_view.y, p_view.y));
+	if (!FILTER) alpha = atan2f(p_view.z, __fsqrt_rn(h2));
+	else alpha = atan2((double)p_view.z, sqrt(max(1e-9, (double)h2)));
 	int p_r_int = beam_lower_bound(beams, alpha, H);
 	float before = 0, after = 0, p_r = 0;
 	if (p_r_int > 0) {
@@ -176,7 +145,7 @@ __device__ __forceinline__ bool project_gaussian(int idx, const float *__restric
 	o.conic = conic;
 	o.u1 = u1;
 	o.u2 = u2;
-	o.s = {p_view.x / dist, p_view.y / dist, p_view.z / dist};
+	o.s = {__fdiv_rn(p_view.x, dist), __fdiv_rn(p_view.y, dist), __fdiv_rn(p_view.z, dist)};
 	o.depth = dist;
 	o.rx = my_radius_x;
 	o.ry = my_radius_y;

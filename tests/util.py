@@ -98,15 +98,23 @@ BWD_TOL = 1e-3   # gradients: ||a - b||_inf / ||b||_inf
 
 
 def assert_forward_close(res, ref, floor=1e-6, max_outlier_frac=0.0, what=""):
-    """res / ref: dicts with color, depth, occ.  Per-element relative gate of SURVEY.md §8d; a fraction of
-    outliers may be allowed when the checker is the CPU oracle (libm vs libdevice ulps)."""
+    """res / ref: dicts with color, depth, occ.  Per-element relative gate of SURVEY.md §8d (1e-4).
+
+    Against the reference CUDA goldens no pixel may exceed it (max_outlier_frac = 0).  When the checker is the
+    CPU oracle, libm and libdevice differ by ulps in exp/sin/cos, so a (pixel, Gaussian) pair sitting exactly on
+    the alpha < 1/255 or T < 1e-4 threshold can decide differently: such a pixel moves by at most one
+    contribution (alpha ~ 1/255).  A small number of those is allowed, each bounded by 2/255 of the image scale."""
     for k in ("color", "depth", "occ"):
-        a, b = np.asarray(res[k]), np.asarray(ref[k])
+        a, b = np.asarray(res[k], np.float64), np.asarray(ref[k], np.float64)
         assert a.shape == b.shape, (what, k, a.shape, b.shape)
         assert np.isfinite(a).all(), (what, k, "non-finite output")
-        e, nout = rel_elem(a, b, floor)
-        assert rel_norm(a, b) <= FWD_TOL, (what, k, "norm-rel", rel_norm(a, b))
-        assert nout <= max_outlier_frac * a.size, (what, k, "elem-rel max", e, "outliers", nout, "of", a.size)
+        err = np.abs(a - b)
+        e = err / np.maximum(np.abs(b), floor)
+        out = e > FWD_TOL
+        allowed = int(max_outlier_frac * a.size) + (2 if max_outlier_frac > 0 else 0)
+        assert int(out.sum()) <= allowed, (what, k, "elem-rel max", float(e.max()), "outliers", int(out.sum()), "of", a.size)
+        if out.any():
+            assert err[out].max() <= 2.0 / 255.0 * max(np.abs(b).max(), 1e-30), (what, k, "outlier too large", float(err[out].max()))
 
 
 def assert_grads_close(grads, ref, skip=(), tol=BWD_TOL, what=""):
