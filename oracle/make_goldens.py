@@ -35,6 +35,12 @@ CASES = {
     "g4_cov_precomp": dict(P=2000, H=16, W=256, seed=14, pose="random", cov_precomp=True),
     "g5_dense_terminate": dict(P=6000, H=4, W=64, seed=15, pose="identity", scale_range=(0.05, 0.2),
                                opacity_range=(0.5, 1.0)),
+    # thousands of entries in ONE depth bucket of every tile, opacities straddling the alpha < 1/255 skip:
+    # threshold-adversarial (a CPU libm cannot reproduce the GPU's ulps there -> `adversarial` flag)
+    "g6_monster_segments": dict(P=8000, H=8, W=64, seed=8, scale_range=(0.3, 1.5), range_m=(10.0, 10.5),
+                                opacity_range=(0.002, 0.02), adversarial=True),
+    # every Gaussian duplicated with bit-identical depth and another colour: order must break ties by index
+    "g7_depth_ties": dict(P=1500, H=8, W=96, seed=9, opacity_range=(0.3, 0.9), duplicate=True),
 }
 
 
@@ -126,19 +132,30 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/goldens")
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated case names (default: all)")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     ref = build_ref.load()
     assert ref is not None, "oracle/_ref/lidargs_ref_C.so missing: run oracle/build_ref.py where /root/reference exists"
     dev = torch.device("cuda:0")
     for name, kw in CASES.items():
+        if a.only and name not in a.only.split(","):
+            continue
         kw = dict(kw)
+        adversarial = kw.pop("adversarial", False)
+        duplicate = kw.pop("duplicate", False)
         covp = kw.pop("cov_precomp", False)
         near = kw.pop("near", 0)
         mod = kw.pop("scale_modifier", 1.0)
         sc = synth.make_scene(**kw)
         sc["near"] = near
         sc["scale_modifier"] = mod
+        if duplicate:
+            for k in ("means3D", "scales", "rotations", "opacities"):
+                sc[k] = np.ascontiguousarray(np.concatenate([sc[k], sc[k]], 0))
+            c2 = np.random.default_rng(kw["seed"]).uniform(0, 1, sc["colors"].shape).astype(np.float32)
+            sc["colors"] = np.ascontiguousarray(np.concatenate([sc["colors"], c2], 0))
+            sc["P"] = sc["means3D"].shape[0]
         sc.update(synth.make_upstream(sc["H"], sc["W"], seed=kw["seed"]))
         cov_pre = cov3d_numpy(sc["scales"], sc["rotations"], mod) if covp else None
         runs = [run_ref(ref, sc, dev, cov_pre) for _ in range(3)]
@@ -149,7 +166,7 @@ def main():
         R = r0["R"]
         pl = r0["binning"].cpu().numpy()[:4 * R].view(np.uint32).copy()
         out = {("in_" + k): v for k, v in sc.items() if isinstance(v, np.ndarray)}
-        out.update(in_far=sc["far"], in_near=sc["near"], in_scale_modifier=sc["scale_modifier"], in_H=H, in_W=W,
+        out.update(adversarial=bool(adversarial), in_far=sc["far"], in_near=sc["near"], in_scale_modifier=sc["scale_modifier"], in_H=H, in_W=W,
                    in_tanfovx=sc["tanfovx"], in_tanfovy=sc["tanfovy"])
         if cov_pre is not None:
             out["in_cov3D_precomp"] = cov_pre
