@@ -43,11 +43,13 @@ scan_bins_kernel(int nbins, uint32_t *__restrict__ cnt, uint32_t *__restrict__ l
 
 // single block: exclusive scan of the per-bin totals (in place: binbase[b] holds total on entry)
 __global__ void __launch_bounds__(1024)
-scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__restrict__ totals)
+scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__restrict__ totals, uint32_t *__restrict__ order)
 {
 	__shared__ unsigned wsum[32];
 	__shared__ unsigned carry_s;
+	__shared__ unsigned hist[33], start[33];
 	if (threadIdx.x == 0) carry_s = 0;
+	if (threadIdx.x < 33) hist[threadIdx.x] = 0;
 	__syncthreads();
 	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	for (int base = 0; base < nbins; base += 1024) {
@@ -69,6 +71,23 @@ scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__rest
 	if (threadIdx.x == 0) {
 		binbase[nbins] = carry_s;
 		totals->num_instances = carry_s;
+	}
+	// launch order of the render kernels: bins by descending size class (floor(log2(count)) + 1), so the
+	// longest lists start first and the tail of the grid is made of short ones
+	__syncthreads();
+	for (int i = threadIdx.x; i < nbins; i += 1024) {
+		unsigned t = binbase[i + 1] - binbase[i];
+		atomicAdd(&hist[t ? 32 - __clz(t) : 0], 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned run = 0;
+		for (int c = 32; c >= 0; c--) { start[c] = run; run += hist[c]; }
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < nbins; i += 1024) {
+		unsigned t = binbase[i + 1] - binbase[i];
+		order[atomicAdd(&start[t ? 32 - __clz(t) : 0], 1u)] = (unsigned)i;
 	}
 }
 
@@ -101,7 +120,7 @@ void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, cudaStream_t st)
 {
 	int warps_per_block = 8;
 	scan_bins_kernel<<<(g.nbins + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(g.nbins, gp.cnt, gp.loc, gp.binbase);
-	scan_total_kernel<<<1, 1024, 0, st>>>(g.nbins, gp.binbase, gp.totals);
+	scan_total_kernel<<<1, 1024, 0, st>>>(g.nbins, gp.binbase, gp.totals, gp.order);
 }
 
 void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, unsigned capacity, cudaStream_t st)

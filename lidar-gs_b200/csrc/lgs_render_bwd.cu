@@ -1,231 +1,280 @@
-// lgs_render_bwd.cu -- back-to-front gradient pass over the lists the forward pass sorted.
+// lgs_render_bwd.cu -- gradient pass over the lists the forward pass sorted.
 //
-// Restates R3 backward.cu:536-791 (renderCUDA).  Same CTA geometry as the forward kernel (one bin of
-// 16 x RB pixels per CTA).  The reference issues 20 scalar float atomics per contributing
-// (pixel, Gaussian) pair; here the 19 gradient components of a pair are reduced across the 32 pixels
-// of a warp with a 21-shuffle transpose-reduce and land in the packed [P, 20] accumulator with one
-// 20-lane RED per (warp, Gaussian).
+// Restates R3 backward.cu:536-791 (renderCUDA).  The reference walks every tile list BACK TO FRONT with one
+// thread per pixel, recovers T by repeated division and issues 20 scalar float atomics per contributing
+// (pixel, Gaussian) pair.  Here the list is replayed FRONT TO BACK, which needs no serial recurrence except
+// the forward pass's own T and colour/depth prefix sums S (bit-identical to forward), because
+//     T_i (c_i - accum_i) = T_i c_i - (C_final - S_i) / (1 - alpha_i)        (accum = the reference's
+//     T_i (1 - accum_o,i) = T_final / (1 - alpha_i)                           running back-to-front blend)
+// so  dL/dalpha_i = T_i q_i - [rem_i - (g_occ - bg.g) T_final] / (1 - alpha_i),
+//     q_i = c_i.g_color + depth_i g_depth,   rem_i = (C_final - S_i).g_color + (D_final - SD_i) g_depth.
+// Per batch of LGS_BATCH entries, same CTA geometry and shared-memory tile as the forward kernel:
+//   1 evaluate : lanes = entries, loop over the group's live pixels -> alpha tile (exact forward arithmetic,
+//                so the contributing pairs are exactly the ones forward blended)
+//   2 scan     : lanes = pixels, serial over the touched entries: T, S -> tile A = dL/dalpha, tile B = alpha T
+//   3 gradient : lanes = entries, loop over live pixels: the 19 gradient components of a Gaussian are summed
+//                over pixels IN REGISTERS (no cross-lane reduction at all) and leave as five 16-byte vector
+//                reductions (red.global.add.v4.f32) into the packed [P, 20] accumulator.
 #include "lgs_common.cuh"
 #include "lgs_kernels.h"
 
 namespace {
 
-// v[0..19] per lane -> one fully warp-reduced component per lane; returns the component index
-// this lane owns (or -1).  21 shuffles instead of 100 for 20 independent butterfly reductions.
-__device__ __forceinline__ int warp_transpose_reduce20(float (&v)[20], float &out)
+template <int RB> struct BwdCfg {
+	static constexpr int NPG = RB >= 2 ? RB / 2 : 1;
+	static constexpr int NEG = LGS_BATCH / 32;
+	static constexpr int NTASK = NPG * NEG;
+	static constexpr int NW = NTASK < 8 ? NTASK : 8;
+	static constexpr int NT = NW * 32;
+	static constexpr size_t TILE = 4 * (size_t)NPG * LGS_BATCH * LGS_TILE_LD;
+	static constexpr size_t O_Q = 0;                                  // 4 x float4[BATCH] record quarters
+	static constexpr size_t O_FEAT = O_Q + 4 * 16 * LGS_BATCH;        // float4 (f0, f1, depth, -)
+	static constexpr size_t O_RAY = O_FEAT + 16 * LGS_BATCH;          // float4 ray per pixel
+	static constexpr size_t O_G = O_RAY + 16 * 32 * NPG;              // float4 (g_color0, g_color1, g_depth, -) per pixel
+	static constexpr size_t O_TA = O_G + 16 * 32 * NPG;
+	static constexpr size_t O_TB = O_TA + TILE;
+	static constexpr size_t O_U = O_TB + TILE;                        // float2 (|u1|^2, |u2|^2)
+	static constexpr size_t O_YP = O_U + 8 * LGS_BATCH;
+	static constexpr size_t O_ID = O_YP + 4 * LGS_BATCH;
+	static constexpr size_t O_LAST = O_ID + 4 * LGS_BATCH;            // last contributor per pixel
+	static constexpr size_t O_MASK = O_LAST + 4 * 32 * NPG;
+	static constexpr size_t O_LIVE = O_MASK + 4 * NPG * NEG;
+	static constexpr size_t O_MAX = O_LIVE + 4 * NPG;
+	static constexpr size_t BYTES = O_MAX + 16;
+};
+
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
 {
-	const unsigned lane = threadIdx.x & 31;
-	const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
-	float w[10], x[5], y[3], z[2];
-#pragma unroll
-	for (int i = 0; i < 10; i++) {
-		float keep = b4 ? v[i + 10] : v[i], send = b4 ? v[i] : v[i + 10];
-		w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-	}
-#pragma unroll
-	for (int i = 0; i < 5; i++) {
-		float keep = b3 ? w[i + 5] : w[i], send = b3 ? w[i] : w[i + 5];
-		x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-	}
-	{
-		float keep = b2 ? x[3] : x[0], send = b2 ? x[0] : x[3];
-		y[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-		keep = b2 ? x[4] : x[1]; send = b2 ? x[1] : x[4];
-		y[1] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-		y[2] = x[2] + __shfl_xor_sync(0xffffffffu, x[2], 4);
-	}
-	{
-		float keep = b1 ? y[1] : y[0], send = b1 ? y[0] : y[1];
-		z[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-		z[1] = y[2] + __shfl_xor_sync(0xffffffffu, y[2], 2);
-	}
-	float keep = b0 ? z[1] : z[0], send = b0 ? z[0] : z[1];
-	out = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-	const int basec = (b4 ? 10 : 0) + (b3 ? 5 : 0);
-	if (!b0) return basec + (b1 ? (b2 ? 4 : 1) : (b2 ? 3 : 0));
-	return (!b1 && !b2) ? basec + 2 : -1; // component 2 of each 5-group is replicated on 4 lanes
+	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-#define BWD_U 4
-
 template <int RB>
-__global__ void __launch_bounds__(RB >= 2 ? 16 * RB : 32)
+__global__ void __launch_bounds__(BwdCfg<RB>::NT)
 render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ binbase,
-		  const uint4 *__restrict__ entries, const float *__restrict__ bg, const float *__restrict__ beams,
-		  const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
-		  const float *__restrict__ dL_dpix, const float *__restrict__ dL_ddepth,
+		  const uint32_t *__restrict__ order, const uint4 *__restrict__ entries, const float *__restrict__ bg,
+		  const float *__restrict__ beams, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
+		  const float4 *__restrict__ fin, const float *__restrict__ dL_dpix, const float *__restrict__ dL_ddepth,
 		  const float *__restrict__ dL_docc, float *__restrict__ grad)
 {
-	constexpr int NT = RB >= 2 ? 16 * RB : 32;
-	constexpr int NW = NT / 32;
-	constexpr int BW = 128; // entries staged per batch
-	__shared__ float4 sq0[BW], sq1[BW], sq2[BW], sq3[BW], sex[BW];
-	__shared__ unsigned char slist[NW][BW];
-	__shared__ unsigned smax[NW];
+	using C = BwdCfg<RB>;
+	constexpr int NT = C::NT, NW = C::NW, NPG = C::NPG, NEG = C::NEG, B = LGS_BATCH, LD = LGS_TILE_LD;
+	extern __shared__ __align__(16) unsigned char smem[];
+	float4 *sq = reinterpret_cast<float4 *>(smem + C::O_Q);
+	float4 *sfeat = reinterpret_cast<float4 *>(smem + C::O_FEAT);
+	float4 *sray = reinterpret_cast<float4 *>(smem + C::O_RAY);
+	float4 *sg = reinterpret_cast<float4 *>(smem + C::O_G);
+	float *tileA = reinterpret_cast<float *>(smem + C::O_TA);
+	float *tileB = reinterpret_cast<float *>(smem + C::O_TB);
+	float2 *su = reinterpret_cast<float2 *>(smem + C::O_U);
+	unsigned *syp = reinterpret_cast<unsigned *>(smem + C::O_YP);
+	unsigned *sid = reinterpret_cast<unsigned *>(smem + C::O_ID);
+	unsigned *slast = reinterpret_cast<unsigned *>(smem + C::O_LAST);
+	unsigned *smask = reinterpret_cast<unsigned *>(smem + C::O_MASK);
+	unsigned *slive = reinterpret_cast<unsigned *>(smem + C::O_LIVE);
+	unsigned *smax = reinterpret_cast<unsigned *>(smem + C::O_MAX);
 
-	const int bin = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int bin = (int)order[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tx = bin % g.gx, rg = bin / g.gx;
-	const int px = tx * LGS_TILE_X_ + (tid & 15), py = rg * RB + (tid >> 4);
-	const bool inside = px < g.W && py < g.H && (tid >> 4) < RB;
-	const int wy0 = rg * RB + 2 * warp, wy1 = wy0 + 2;
 	const unsigned base = binbase[bin];
-	const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
-
-	PixelRay ray = {0.f, 0.f, 0.f};
-	float T_final = 0.f, g0 = 0.f, g1 = 0.f, gd = 0.f, go = 0.f;
-	unsigned last_contributor = 0;
-	if (inside) {
-		ray = lgs_pixel_ray(px, py, g.W, g.H, beams);
-		T_final = final_T[pix];
-		last_contributor = n_contrib[pix];
-		g0 = dL_dpix[pix];
-		g1 = dL_dpix[HW + pix];
-		gd = dL_ddepth[pix];
-		go = dL_docc[pix];
-	}
-	const float bgdot = bg[0] * g0 + bg[1] * g1;
-	float T = T_final;
-	float accum_c0 = 0.f, accum_c1 = 0.f, accum_d = 0.f, accum_o = 0.f;
-	float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_d = 0.f;
-
-	// deepest contributor over the warp (compaction bound) and over the bin (loop bound)
-	unsigned wmax = last_contributor;
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-	if (lane == 0) smax[warp] = wmax;
+	if (tid == 0) smax[0] = 0;
 	__syncthreads();
-	unsigned maxc = 0;
-#pragma unroll
-	for (int i = 0; i < NW; i++) maxc = max(maxc, smax[i]);
 
-	for (int hi = (int)maxc; hi > 0; hi -= BW) {
-		const int lo = max(0, hi - BW), bn = hi - lo;
-		__syncthreads();
-		for (int j = tid; j < bn; j += NT) {
-			uint4 e = entries[base + lo + j];
-			const float4 *r = rec + 4 * (size_t)e.y;
-			float4 a = r[0], b = r[1], c = r[2], d = r[3];
-			sq0[j] = a; sq1[j] = b; sq2[j] = c; sq3[j] = d;
-			sex[j] = make_float4(lgs_dot_self(c.x, c.y, c.z), lgs_dot_self(d.x, d.y, d.z), __uint_as_float(e.z),
-					     __uint_as_float(e.y));
+	// scan state: warp w < NPG owns pixel group w, lane = pixel
+	const int px = tx * LGS_TILE_X_ + (lane & 15), py = rg * RB + 2 * warp + (lane >> 4);
+	const bool blender = warp < NPG;
+	const bool inside = blender && px < g.W && py < g.H && 2 * warp + (lane >> 4) < RB;
+	float T = 1.f, S0 = 0.f, S1 = 0.f, SD = 0.f;
+	float Tf = 0.f, C0f = 0.f, C1f = 0.f, Df = 0.f, g0 = 0.f, g1 = 0.f, gd = 0.f, kocc = 0.f;
+	unsigned lastc = 0;
+	if (blender) {
+		PixelRay ray = {0.f, 0.f, 0.f};
+		if (inside) {
+			const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
+			ray = lgs_pixel_ray(px, py, g.W, g.H, beams);
+			Tf = final_T[pix];
+			lastc = n_contrib[pix];
+			const float4 f = fin[pix];
+			C0f = f.x; C1f = f.y; Df = f.z;
+			g0 = dL_dpix[pix];
+			g1 = dL_dpix[HW + pix];
+			gd = dL_ddepth[pix];
+			const float go = dL_docc[pix];
+			kocc = (go - (bg[0] * g0 + bg[1] * g1)) * Tf; // occ + background terms, both ~ T_final / (1 - alpha)
+		}
+		sray[warp * 32 + lane] = make_float4(ray.x, ray.y, ray.z, 0.f);
+		sg[warp * 32 + lane] = make_float4(g0, g1, gd, 0.f);
+		slast[warp * 32 + lane] = lastc;
+		unsigned wmax = lastc;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+		if (lane == 0) atomicMax(&smax[0], wmax);
+	}
+	__syncthreads();
+	const unsigned maxc = smax[0]; // deepest contributor of the bin: nothing behind it is replayed
+
+	for (unsigned lo = 0; lo < maxc; lo += B) {
+		const int bn = (int)min((unsigned)B, maxc - lo);
+		__syncthreads(); // previous batch fully consumed
+		for (int i = tid; i < 4 * bn; i += NT) {
+			const int j = i >> 2, part = i & 3;
+			const uint4 e = entries[base + lo + j];
+			const float4 q = rec[4 * (size_t)e.y + part];
+			sq[part * B + j] = q;
+			if (part == 0) { syp[j] = e.z; sid[j] = e.y; }
+			else if (part == 1) sfeat[j].z = q.w;
+			else if (part == 2) { sfeat[j].x = q.w; su[j].x = lgs_dot_self(q.x, q.y, q.z); }
+			else { sfeat[j].y = q.w; su[j].y = lgs_dot_self(q.x, q.y, q.z); }
+		}
+		const bool lane_live = lastc > lo;
+		if (blender) {
+			const unsigned lv = __ballot_sync(0xffffffffu, lane_live);
+			if (lane == 0) slive[warp] = lv;
 		}
 		__syncthreads();
-		// per-warp compaction, back to front: entries in this warp's rows and not beyond its deepest contributor
-		int nl = 0;
-		for (int j0 = 0; j0 < bn; j0 += 32) {
-			const int j = bn - 1 - (j0 + lane);
-			bool hit = false;
-			if (j >= 0 && (unsigned)(lo + j) < wmax) {
-				const unsigned yp = __float_as_uint(sex[j].z);
-				hit = (int)(yp & 0xffffu) < wy1 && (int)(yp >> 16) > wy0;
+
+		// ---- 1: evaluate alpha, lanes = entries ----
+		for (int task = warp; task < C::NTASK; task += NW) {
+			const int pg = task % NPG, eg = task / NPG;
+			unsigned lv = slive[pg];
+			if (eg * 32 >= bn || lv == 0) {
+				if (lane == 0) smask[pg * NEG + eg] = 0;
+				continue;
 			}
-			const unsigned mask = __ballot_sync(0xffffffffu, hit);
-			if (hit) slist[warp][nl + __popc(mask & ((1u << lane) - 1))] = (unsigned char)j;
-			nl += __popc(mask);
+			const int j = eg * 32 + lane;
+			const bool valid = j < bn;
+			const int jj = valid ? j : 0;
+			const float4 a = sq[jj], b = sq[B + jj], c = sq[2 * B + jj], d = sq[3 * B + jj];
+			const float2 uu = su[jj];
+			const unsigned yp = syp[jj];
+			const int ya = (int)(yp & 0xffffu), yb = (int)(yp >> 16);
+			const int row0 = rg * RB + 2 * pg;
+			const bool r0 = valid && row0 >= ya && row0 < yb, r1 = valid && row0 + 1 >= ya && row0 + 1 < yb;
+			float *trow = tileA + (size_t)(pg * B + j) * LD;
+			const float4 *rays = sray + pg * 32;
+			const unsigned *lasts = slast + pg * 32;
+			const unsigned pos = lo + (unsigned)j;
+			bool any = false;
+			while (lv) {
+				const int p = __ffs(lv) - 1;
+				lv &= lv - 1;
+				const float4 rr = rays[p];
+				float alpha = 0.f;
+				if (((p < 16) ? r0 : r1) && pos < lasts[p]) {
+					const PixelRay ray = {rr.x, rr.y, rr.z};
+					float dx, dy, ex_, ey_, ez_, du1, du2, G = 0.f;
+					const bool ok = lgs_pair_eval(ray, b.x, b.y, b.z, c.x, c.y, c.z, d.x, d.y, d.z, uu.x, uu.y, a.x, a.y,
+								      a.z, dx, dy, ex_, ey_, ez_, du1, du2, G);
+					const float al = fminf(0.99f, __fmul_rn(a.w, G));
+					alpha = (ok && !(al < 1.0f / 255.0f)) ? al : 0.f;
+				}
+				if (valid) trow[p] = alpha;
+				any |= alpha != 0.f;
+			}
+			const unsigned m32 = __ballot_sync(0xffffffffu, any);
+			if (lane == 0) smask[pg * NEG + eg] = m32;
 		}
-		__syncwarp();
-		for (int l0 = 0; l0 < nl; l0 += BWD_U) {
-			// phase A (independent): geometry + alpha of BWD_U pairs
-			float alpha[BWD_U], Gv[BWD_U], dxv[BWD_U], dyv[BWD_U], du1v[BWD_U], du2v[BWD_U];
-			float ddx[BWD_U], ddy[BWD_U], ddz[BWD_U], dLda[BWD_U], dch[BWD_U];
-			int jj[BWD_U];
+		__syncthreads();
+
+		// ---- 2: scan, lanes = pixels ----
+		if (blender && slive[warp] != 0) {
+			float *ta = tileA + (size_t)(warp * B) * LD + lane;
+			float *tb = tileB + (size_t)(warp * B) * LD + lane;
 #pragma unroll
-			for (int u = 0; u < BWD_U; u++) {
-				alpha[u] = 0.f;
-				jj[u] = 0;
-				Gv[u] = dxv[u] = dyv[u] = du1v[u] = du2v[u] = ddx[u] = ddy[u] = ddz[u] = 0.f;
-				if (l0 + u < nl) {
-					const int j = slist[warp][l0 + u];
-					jj[u] = j;
-					const float4 ex = sex[j];
-					const unsigned yp = __float_as_uint(ex.z);
-					const float4 a = sq0[j], b = sq1[j], c = sq2[j], d = sq3[j];
-					const bool ok = lgs_pair_eval(ray, b.x, b.y, b.z, c.x, c.y, c.z, d.x, d.y, d.z, ex.x, ex.y,
-								      a.x, a.y, a.z, dxv[u], dyv[u], ddx[u], ddy[u], ddz[u], du1v[u],
-								      du2v[u], Gv[u]);
-					const float al = fminf(0.99f, __fmul_rn(a.w, Gv[u]));
-					const bool mine = (unsigned)(lo + j) < last_contributor && py >= (int)(yp & 0xffffu) &&
-							  py < (int)(yp >> 16);
-					alpha[u] = (ok && mine && !(al < 1.0f / 255.0f)) ? al : 0.f;
+			for (int eg = 0; eg < NEG; eg++) {
+				unsigned mw = smask[warp * NEG + eg];
+				while (mw) {
+					const int j = eg * 32 + __ffs(mw) - 1;
+					mw &= mw - 1;
+					const float alpha = lane_live ? ta[(size_t)j * LD] : 0.f;
+					const float4 f = sfeat[j];
+					float w = 0.f, dLda = 0.f;
+					if (alpha != 0.f) {
+						const float om = __fsub_rn(1.0f, alpha);
+						const float r = __frcp_rn(om);
+						w = alpha * T;
+						// forward's own accumulation order: S_i == forward's running C at this entry
+						S0 = __fmaf_rn(T, __fmul_rn(alpha, f.x), S0);
+						S1 = __fmaf_rn(T, __fmul_rn(alpha, f.y), S1);
+						SD = __fmaf_rn(T, __fmul_rn(alpha, f.z), SD);
+						const float q = f.x * g0 + f.y * g1 + f.z * gd;
+						const float rem = (C0f - S0) * g0 + (C1f - S1) * g1 + (Df - SD) * gd;
+						dLda = T * q - (rem - kocc) * r;
+						T = __fmul_rn(T, om);
+					}
+					ta[(size_t)j * LD] = dLda;
+					tb[(size_t)j * LD] = w;
 				}
 			}
-			// phase B (serial in T and the running accumulators): bwd.cu:681-727
-#pragma unroll
-			for (int u = 0; u < BWD_U; u++) {
-				dLda[u] = 0.f;
-				dch[u] = 0.f;
-				if (alpha[u] != 0.f) {
-					const int j = jj[u];
-					const float al = alpha[u], c0 = sq2[j].w, c1 = sq3[j].w, dep = sq1[j].w;
-					T = T / (1.f - al);
-					dch[u] = al * T;
-					float dL_dalpha = 0.f;
-					accum_c0 = last_alpha * last_c0 + (1.f - last_alpha) * accum_c0;
-					last_c0 = c0;
-					dL_dalpha += (c0 - accum_c0) * g0;
-					accum_c1 = last_alpha * last_c1 + (1.f - last_alpha) * accum_c1;
-					last_c1 = c1;
-					dL_dalpha += (c1 - accum_c1) * g1;
-					accum_d = last_alpha * last_d + (1.f - last_alpha) * accum_d;
-					last_d = dep;
-					dL_dalpha += (dep - accum_d) * gd;
-					accum_o = last_alpha + (1.f - last_alpha) * accum_o;
-					dL_dalpha += (1.f - accum_o) * go;
-					dL_dalpha *= T;
-					last_alpha = al;
-					dL_dalpha += (-T_final / (1.f - al)) * bgdot;
-					dLda[u] = dL_dalpha;
-				}
+		}
+		__syncthreads();
+
+		// ---- 3: gradients, lanes = entries, sums over pixels stay in registers ----
+		for (int task = warp; task < C::NTASK; task += NW) {
+			const int pg = task % NPG, eg = task / NPG;
+			const unsigned m32 = smask[pg * NEG + eg];
+			if (!((m32 >> lane) & 1u)) continue;
+			unsigned lv = slive[pg];
+			const int j = eg * 32 + lane;
+			const float4 a = sq[j], b = sq[B + j], c = sq[2 * B + j], d = sq[3 * B + j];
+			const float2 uu = su[j];
+			const float r11 = 1.f / uu.x, r22 = 1.f / uu.y;
+			const float ab = (c.x * d.x + c.y * d.y + c.z * d.z) * r11 * r22; // (u1/|u1|^2) . (u2/|u2|^2)
+			const float *ta = tileA + (size_t)(pg * B + j) * LD;
+			const float *tb = tileB + (size_t)(pg * B + j) * LD;
+			const float4 *rays = sray + pg * 32, *gs = sg + pg * 32;
+			float sKx = 0.f, sKy = 0.f, sM = 0.f, aXx = 0.f, aXy = 0.f, aXz = 0.f, aXu = 0.f, aYx = 0.f, aYy = 0.f,
+			      aYz = 0.f, aYu = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, opa = 0.f, col0 = 0.f, col1 = 0.f, dep = 0.f;
+			while (lv) {
+				const int p = __ffs(lv) - 1;
+				lv &= lv - 1;
+				const float w = tb[p];
+				if (w == 0.f) continue;
+				const float dLda = ta[p];
+				const float4 rr = rays[p], gg = gs[p];
+				const float ddx = b.x - rr.x, ddy = b.y - rr.y, ddz = b.z - rr.z;
+				const float du1 = ddx * c.x + ddy * c.y + ddz * c.z, du2 = ddx * d.x + ddy * d.y + ddz * d.z;
+				const float dx = du1 * r11, dy = du2 * r22;
+				const float G = __expf(-0.5f * (a.x * dx * dx + a.z * dy * dy) - a.y * dx * dy);
+				const float dL_dG = a.w * dLda;
+				const float gdx = G * dx, gdy = G * dy;
+				const float kx = dL_dG * (-gdx * a.x - gdy * a.y), ky = dL_dG * (-gdy * a.z - gdx * a.y);
+				sKx += kx; sKy += ky;
+				aXx += kx * ddx; aXy += kx * ddy; aXz += kx * ddz; aXu += kx * du1;
+				aYx += ky * ddx; aYy += ky * ddy; aYz += ky * ddz; aYu += ky * du2;
+				const float n2 = kx * (kx * r11 + 2.f * ky * ab) + ky * ky * r22; // |dL/d(sphere mean)|^2 of this pair
+				sM += n2 > 0.f ? n2 * rsqrtf(n2) : 0.f;
+				const float t1 = gdx * dL_dG, t2 = gdy * dL_dG;
+				cA += t1 * dx; cB += t1 * dy; cC += t2 * dy;
+				opa += G * dLda;
+				col0 += w * gg.x; col1 += w * gg.y; dep += w * gg.z;
 			}
-			// phase C (independent): per-pair gradients, warp reduce, one 19-lane RED per (warp, Gaussian)
-#pragma unroll
-			for (int u = 0; u < BWD_U; u++) {
-				if (__ballot_sync(0xffffffffu, alpha[u] != 0.f) == 0) continue;
-				const int j = jj[u];
-				float v[20];
-#pragma unroll
-				for (int i = 0; i < 20; i++) v[i] = 0.f;
-				if (alpha[u] != 0.f) { // bwd.cu:731-788
-					const float4 ex = sex[j];
-					const float4 a = sq0[j], c = sq2[j], d = sq3[j];
-					const float u11 = ex.x, u22 = ex.y, G = Gv[u], dx = dxv[u], dy = dyv[u];
-					const float dL_dG = a.w * dLda[u];
-					const float gdx = G * dx, gdy = G * dy;
-					const float dG_dx = -gdx * a.x - gdy * a.y;
-					const float dG_dy = -gdy * a.z - gdx * a.y;
-					const float kx = dL_dG * dG_dx, ky = dL_dG * dG_dy;
-					const float r11 = 1.f / u11, r22 = 1.f / u22;
-					const float i11 = r11 * r11, i22 = r22 * r22;
-					v[G_COL0] = dch[u] * g0;
-					v[G_COL1] = dch[u] * g1;
-					v[G_DEP] = dch[u] * gd;
-					v[G_U1 + 0] = kx * ((ddx[u] * u11 - du1v[u] * 2 * c.x) * i11);
-					v[G_U1 + 1] = kx * ((ddy[u] * u11 - du1v[u] * 2 * c.y) * i11);
-					v[G_U1 + 2] = kx * ((ddz[u] * u11 - du1v[u] * 2 * c.z) * i11);
-					v[G_U2 + 0] = ky * ((ddx[u] * u22 - du2v[u] * 2 * d.x) * i22);
-					v[G_U2 + 1] = ky * ((ddy[u] * u22 - du2v[u] * 2 * d.y) * i22);
-					v[G_U2 + 2] = ky * ((ddz[u] * u22 - du2v[u] * 2 * d.z) * i22);
-					v[G_M2X] = kx;
-					v[G_M2Y] = ky;
-					const float sx = dL_dG * (dG_dx * (c.x * r11) + dG_dy * (d.x * r22));
-					const float sy = dL_dG * (dG_dx * (c.y * r11) + dG_dy * (d.y * r22));
-					const float sz = dL_dG * (dG_dx * (c.z * r11) + dG_dy * (d.z * r22));
-					v[G_SPH + 0] = sx;
-					v[G_SPH + 1] = sy;
-					v[G_SPH + 2] = sz;
-					v[G_M2Z] = sqrtf(sx * sx + sy * sy + sz * sz);
-					v[G_CONA] = -0.5f * gdx * dx * dL_dG;
-					v[G_CONB] = -0.5f * gdx * dy * dL_dG;
-					v[G_CONC] = -0.5f * gdy * dy * dL_dG;
-					v[G_OPA] = G * dLda[u];
-				}
-				float red;
-				const int comp = warp_transpose_reduce20(v, red);
-				if (comp >= 0 && comp != G_PAD)
-					atomicAdd(grad + (size_t)__float_as_uint(sex[j].w) * LGS_GRAD_STRIDE + comp, red);
-			}
+			float *row = grad + (size_t)sid[j] * LGS_GRAD_STRIDE;
+			const float i11 = r11 * r11, i22 = r22 * r22;
+			// component order: G_M2X.. in lgs_common.cuh
+			red_add_v4(row + 0, sKx, sKy, sM, -0.5f * cA);
+			red_add_v4(row + 4, -0.5f * cB, -0.5f * cC, opa, col0);
+			red_add_v4(row + 8, col1, dep, c.x * r11 * sKx + d.x * r22 * sKy, c.y * r11 * sKx + d.y * r22 * sKy);
+			red_add_v4(row + 12, c.z * r11 * sKx + d.z * r22 * sKy, i11 * (uu.x * aXx - 2.f * c.x * aXu),
+				   i11 * (uu.x * aXy - 2.f * c.y * aXu), i11 * (uu.x * aXz - 2.f * c.z * aXu));
+			red_add_v4(row + 16, i22 * (uu.y * aYx - 2.f * d.x * aYu), i22 * (uu.y * aYy - 2.f * d.y * aYu),
+				   i22 * (uu.y * aYz - 2.f * d.z * aYu), 0.f);
 		}
 	}
+}
+
+template <int RB>
+void launch_bwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, const uint4 *entries, const float *bg,
+		const float *beams, const float *dL_dpix, const float *dL_ddepth, const float *dL_docc, float *grad,
+		cudaStream_t st)
+{
+	using C = BwdCfg<RB>;
+	static bool configured = false;
+	if (!configured) {
+		cudaFuncSetAttribute(render_bwd_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+		configured = true;
+	}
+	render_bwd_kernel<RB><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.binbase, gp.order, entries, bg, beams, ip.final_T,
+								 ip.n_contrib, ip.fin, dL_dpix, dL_ddepth, dL_docc, grad);
 }
 
 } // namespace
@@ -234,15 +283,11 @@ void lgs_launch_render_bwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePt
 			   const float *bg, const float *beams, const float *dL_dpix, const float *dL_ddepth,
 			   const float *dL_docc, float *grad, cudaStream_t st)
 {
-#define LAUNCH(RB_)                                                                                              \
-	render_bwd_kernel<RB_><<<g.nbins, (RB_ >= 2 ? 16 * RB_ : 32), 0, st>>>(g, gp.rec, gp.binbase, entries, bg, beams, \
-							      ip.final_T, ip.n_contrib, dL_dpix, dL_ddepth, dL_docc, grad)
 	switch (g.RB) {
-	case 1: LAUNCH(1); break;
-	case 2: LAUNCH(2); break;
-	case 4: LAUNCH(4); break;
-	case 8: LAUNCH(8); break;
-	default: LAUNCH(16); break;
+	case 1: launch_bwd<1>(g, gp, ip, entries, bg, beams, dL_dpix, dL_ddepth, dL_docc, grad, st); break;
+	case 2: launch_bwd<2>(g, gp, ip, entries, bg, beams, dL_dpix, dL_ddepth, dL_docc, grad, st); break;
+	case 4: launch_bwd<4>(g, gp, ip, entries, bg, beams, dL_dpix, dL_ddepth, dL_docc, grad, st); break;
+	case 8: launch_bwd<8>(g, gp, ip, entries, bg, beams, dL_dpix, dL_ddepth, dL_docc, grad, st); break;
+	default: launch_bwd<16>(g, gp, ip, entries, bg, beams, dL_dpix, dL_ddepth, dL_docc, grad, st); break;
 	}
-#undef LAUNCH
 }

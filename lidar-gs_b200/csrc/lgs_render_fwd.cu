@@ -2,24 +2,33 @@
 //
 // Restates R3 forward.cu:503-641 (renderCUDA) and the per-tile ordering that the reference gets from
 // cub::DeviceRadixSortPairs on tile|depth keys (rasterizer_impl.cu:317-322).  One CTA owns one bin
-// (16 columns x RB rows of pixels, one thread per pixel).  It walks the bin's depth buckets front to
-// back; consecutive buckets are grouped into segments of <= LGS_SEG_CAP entries, each segment is
-// sorted in shared memory on (depth bits, Gaussian idx) -- the tie-break a stable LSD sort over
-// idx-ordered input gives -- written back in place (the backward pass replays it), and composited
-// in batches of LGS_BATCH packed 64-B records staged in shared memory.  As soon as every pixel of
-// the bin has hit the reference's T < 1e-4 stop the CTA quits: buckets behind the stop are never
-// read, sorted or gathered.
+// (16 columns x RB rows of pixels).  It walks the bin's depth buckets front to back; consecutive buckets
+// are grouped into segments, each segment is sorted in shared memory on (depth bits, Gaussian idx) -- the
+// tie-break a stable LSD sort over idx-ordered input gives -- written back in place (the backward pass
+// replays it) and composited in batches of LGS_BATCH entries.  As soon as every pixel of the bin has hit
+// the reference's T < 1e-4 stop the CTA quits: buckets behind the stop are never read, sorted or gathered.
+//
+// Compositing a batch is split into the part that is parallel and the part that is not:
+//   evaluate : alpha of every (entry, live pixel) pair.  LANES ARE ENTRIES, the loop runs over the live
+//              pixels of a 32-pixel group: the 64-B record stays in registers, the pixel's ray is a
+//              shared-memory broadcast, terminated pixels cost nothing (the reference -- and a
+//              lane-per-pixel loop -- keeps evaluating whole warps for a single straggler pixel).
+//              Results go to an alpha tile in shared memory (row stride 33: conflict-free both ways).
+//   blend    : LANES ARE PIXELS, serial over the entries that have a non-zero alpha for the group:
+//              T, colour, depth -- ~a dozen instructions per entry, in exactly the reference's order.
+// Same (pixel, Gaussian) pairs, same arithmetic per pair, same blend order => bit-identical images.
 #include "lgs_common.cuh"
 #include "lgs_kernels.h"
 
 namespace {
 
 #define SEG_TARGET 256
+#define RANK_SORT_MAX 256
 
 // Bitonic network for arbitrary n (all compare-exchanges ascending, first step of each merge
 // mirrored), so no padding to a power of two is needed: pairs whose upper index is >= n are skipped.
-template <int NT, typename KeyArr, typename ValArr>
-__device__ __forceinline__ void bitonic_sort_any(KeyArr key, ValArr val, int n, int tid)
+template <int NT>
+__device__ __forceinline__ void bitonic_sort_any(unsigned long long *key, unsigned *val, int n, int tid)
 {
 	int n2 = 1;
 	while (n2 < n) n2 <<= 1;
@@ -83,9 +92,9 @@ __device__ void bitonic_sort_global(uint4 *e, int n, int tid)
 	}
 }
 
-// Small segments (the common case): rank sort.  Every thread counts, for each of its entries, how many
-// keys of the segment are smaller -- broadcast shared-memory reads, no barriers inside, ILP-friendly --
-// and scatters the entry to that rank.  Keys are unique (the Gaussian index is part of the key).
+// Small segments (the common case): rank sort.  Every thread counts, for its entry, how many keys of the
+// segment are smaller -- broadcast shared-memory reads, no barriers inside -- and scatters the entry to
+// that rank.  Keys are unique (the Gaussian index is part of the key).
 template <int NT>
 __device__ __forceinline__ void rank_sort_small(const unsigned long long *__restrict__ key, const unsigned *__restrict__ val,
 						unsigned long long *__restrict__ okey, unsigned *__restrict__ oval, int n, int tid)
@@ -105,41 +114,75 @@ __device__ __forceinline__ void rank_sort_small(const unsigned long long *__rest
 	}
 }
 
-#define RANK_SORT_MAX 256
-#define EVAL_U 4
+template <int RB> struct FwdCfg {
+	static constexpr int NPG = RB >= 2 ? RB / 2 : 1;     // 32-pixel groups (2 rows x 16 columns)
+	static constexpr int NEG = LGS_BATCH / 32;            // 32-entry groups per batch
+	static constexpr int NTASK = NPG * NEG;               // evaluate tasks per batch
+	static constexpr int NW = NTASK < 8 ? NTASK : 8;      // warps per CTA (>= NPG for every RB)
+	static constexpr int NT = NW * 32;
+	// dynamic shared memory carve-up (bytes)
+	static constexpr size_t O_KEYA = 0;
+	static constexpr size_t O_KEYB = O_KEYA + 8 * LGS_SEG_CAP;
+	static constexpr size_t O_Q = O_KEYB + 8 * RANK_SORT_MAX;            // 4 x float4[BATCH] record quarters
+	static constexpr size_t O_FEAT = O_Q + 4 * 16 * LGS_BATCH;            // float4 (f0, f1, depth, -)
+	static constexpr size_t O_RAY = O_FEAT + 16 * LGS_BATCH;              // float4 per pixel of every group
+	static constexpr size_t O_TILE = O_RAY + 16 * 32 * NPG;               // alpha tile
+	static constexpr size_t O_VALA = O_TILE + 4 * (size_t)NPG * LGS_BATCH * LGS_TILE_LD;
+	static constexpr size_t O_VALB = O_VALA + 4 * LGS_SEG_CAP;
+	static constexpr size_t O_U = O_VALB + 4 * RANK_SORT_MAX;             // float2 (|u1|^2, |u2|^2)
+	static constexpr size_t O_YP = O_U + 8 * LGS_BATCH;                   // y0 | y1 << 16
+	static constexpr size_t O_MASK = O_YP + 4 * LGS_BATCH;                // per (group, entry group): entries with alpha != 0
+	static constexpr size_t O_LIVE = O_MASK + 4 * NPG * NEG;              // per group: pixels not yet terminated
+	static constexpr size_t O_LOC = O_LIVE + 4 * NPG;
+	static constexpr size_t BYTES = O_LOC + 4 * (LGS_NB + 1);
+};
 
 template <int RB>
-__global__ void __launch_bounds__(RB >= 2 ? 16 * RB : 32)
+__global__ void __launch_bounds__(FwdCfg<RB>::NT)
 render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ loc,
-		  const uint32_t *__restrict__ binbase, uint4 *__restrict__ entries,
+		  const uint32_t *__restrict__ binbase, const uint32_t *__restrict__ order, uint4 *__restrict__ entries,
 		  const float *__restrict__ bg, const float *__restrict__ beams,
 		  float *__restrict__ final_T, uint32_t *__restrict__ n_contrib, uint32_t *__restrict__ sorted_end,
-		  float *__restrict__ out_color, float *__restrict__ out_depth, float *__restrict__ out_occ, int sort_all)
+		  float4 *__restrict__ fin, float *__restrict__ out_color, float *__restrict__ out_depth,
+		  float *__restrict__ out_occ, int sort_all)
 {
-	constexpr int NT = RB >= 2 ? 16 * RB : 32; // RB == 1 (tests only): upper half-warp idles
-	constexpr int NW = NT / 32;
-	__shared__ unsigned long long skeyA[LGS_SEG_CAP];
-	__shared__ unsigned svalA[LGS_SEG_CAP];
-	__shared__ unsigned long long skeyB[RANK_SORT_MAX];
-	__shared__ unsigned svalB[RANK_SORT_MAX];
-	__shared__ float4 sq0[LGS_BATCH], sq1[LGS_BATCH], sq2[LGS_BATCH], sq3[LGS_BATCH], sex[LGS_BATCH];
-	__shared__ unsigned char slist[NW][LGS_BATCH]; // per warp: batch entries whose row range meets the warp's 2 rows
-	__shared__ unsigned sloc[LGS_NB + 1];
+	using C = FwdCfg<RB>;
+	constexpr int NT = C::NT, NW = C::NW, NPG = C::NPG, NEG = C::NEG, B = LGS_BATCH, LD = LGS_TILE_LD;
+	extern __shared__ __align__(16) unsigned char smem[];
+	unsigned long long *skeyA = reinterpret_cast<unsigned long long *>(smem + C::O_KEYA);
+	unsigned long long *skeyB = reinterpret_cast<unsigned long long *>(smem + C::O_KEYB);
+	float4 *sq = reinterpret_cast<float4 *>(smem + C::O_Q); // sq[part * B + j]
+	float4 *sfeat = reinterpret_cast<float4 *>(smem + C::O_FEAT);
+	float4 *sray = reinterpret_cast<float4 *>(smem + C::O_RAY);
+	float *tile = reinterpret_cast<float *>(smem + C::O_TILE);
+	unsigned *svalA = reinterpret_cast<unsigned *>(smem + C::O_VALA);
+	unsigned *svalB = reinterpret_cast<unsigned *>(smem + C::O_VALB);
+	float2 *su = reinterpret_cast<float2 *>(smem + C::O_U);
+	unsigned *syp = reinterpret_cast<unsigned *>(smem + C::O_YP);
+	unsigned *smask = reinterpret_cast<unsigned *>(smem + C::O_MASK);
+	unsigned *slive = reinterpret_cast<unsigned *>(smem + C::O_LIVE);
+	unsigned *sloc = reinterpret_cast<unsigned *>(smem + C::O_LOC);
 
-	const int bin = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int bin = (int)order[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tx = bin % g.gx, rg = bin / g.gx;
-	const int px = tx * LGS_TILE_X_ + (tid & 15), py = rg * RB + (tid >> 4);
-	const bool inside = px < g.W && py < g.H && (tid >> 4) < RB;
-	const int wy0 = rg * RB + 2 * warp, wy1 = wy0 + 2; // rows covered by this warp: [wy0, wy1)
 	const unsigned base = binbase[bin], ntotal = binbase[bin + 1] - base;
 	for (int i = tid; i < LGS_NB; i += NT) sloc[i] = loc[(size_t)bin * LGS_NB + i];
 	if (tid == 0) sloc[LGS_NB] = ntotal;
 
-	PixelRay ray = {0.f, 0.f, 0.f};
-	if (inside) ray = lgs_pixel_ray(px, py, g.W, g.H, beams);
+	// blend state: warp w < NPG owns pixel group w, lane = pixel (row 2w + lane/16, column lane%16)
+	const int px = tx * LGS_TILE_X_ + (lane & 15), py = rg * RB + 2 * warp + (lane >> 4);
+	const bool blender = warp < NPG;
+	const bool inside = blender && px < g.W && py < g.H && 2 * warp + (lane >> 4) < RB;
 	float T = 1.0f, C0 = 0.f, C1 = 0.f, D = 0.f;
 	unsigned last = 0;
 	bool done = !inside;
+	if (blender) {
+		PixelRay ray = {0.f, 0.f, 0.f};
+		if (inside) ray = lgs_pixel_ray(px, py, g.W, g.H, beams);
+		sray[warp * 32 + lane] = make_float4(ray.x, ray.y, ray.z, 0.f);
+		const unsigned lv = __ballot_sync(0xffffffffu, inside);
+		if (lane == 0) slive[warp] = lv;
+	}
 	bool all_done = false;
 	__syncthreads();
 
@@ -156,6 +199,14 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			if (n >= SEG_TARGET) break;
 		}
 		if (n == 0) { k = k2; continue; }
+		__syncthreads(); // slive is final for everything composited so far
+		if (!all_done) {
+			unsigned any_live = 0;
+#pragma unroll
+			for (int i = 0; i < NPG; i++) any_live |= slive[i];
+			all_done = any_live == 0;
+		}
+		if (all_done && !sort_all) break; // nothing behind this point is read, sorted or gathered
 		uint4 *seg = entries + base + s0;
 		const bool oversized = n > LGS_SEG_CAP;
 		if (oversized) bitonic_sort_global<NT>(seg, (int)n, tid);
@@ -187,77 +238,98 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			}
 			if (all_done) continue; // sort_all mode: keep sorting, nothing left to blend
 			// ---- composite the m sorted entries in batches ----
-			for (int b0 = 0; b0 < m; b0 += LGS_BATCH) {
-				const int bn = min(LGS_BATCH, m - b0);
-				__syncthreads(); // previous batch fully consumed
-				for (int j = tid; j < bn; j += NT) {
-					unsigned id = (unsigned)skey[b0 + j];
-					const float4 *r = rec + 4 * (size_t)id;
-					float4 a = r[0], b = r[1], c = r[2], d = r[3];
-					sq0[j] = a; sq1[j] = b; sq2[j] = c; sq3[j] = d;
-					sex[j] = make_float4(lgs_dot_self(c.x, c.y, c.z), lgs_dot_self(d.x, d.y, d.z),
-							     __uint_as_float(sval[b0 + j]), __uint_as_float(id));
+			for (int b0 = 0; b0 < m; b0 += B) {
+				const int bn = min(B, m - b0);
+				__syncthreads(); // previous batch fully consumed; slive final
+				{
+					unsigned any_live = 0;
+#pragma unroll
+					for (int i = 0; i < NPG; i++) any_live |= slive[i];
+					if (any_live == 0) { all_done = true; break; }
 				}
-				// per-warp compaction of the entries whose row range meets this warp's rows
-				int nl = 0;
-				for (int j0 = 0; j0 < bn; j0 += 32) {
-					const int j = j0 + lane;
-					bool hit = false;
-					if (j < bn) {
-						const unsigned yp = sval[b0 + j];
-						hit = (int)(yp & 0xffffu) < wy1 && (int)(yp >> 16) > wy0;
-					}
-					const unsigned mask = __ballot_sync(0xffffffffu, hit);
-					if (hit) slist[warp][nl + __popc(mask & ((1u << lane) - 1))] = (unsigned char)j;
-					nl += __popc(mask);
+				// stage the batch: one float4 (a quarter record) per thread
+				for (int i = tid; i < 4 * bn; i += NT) {
+					const int j = i >> 2, part = i & 3;
+					const unsigned id = (unsigned)skey[b0 + j];
+					const float4 q = rec[4 * (size_t)id + part];
+					sq[part * B + j] = q;
+					if (part == 0) syp[j] = sval[b0 + j];
+					else if (part == 1) sfeat[j].z = q.w;
+					else if (part == 2) { sfeat[j].x = q.w; su[j].x = lgs_dot_self(q.x, q.y, q.z); }
+					else { sfeat[j].y = q.w; su[j].y = lgs_dot_self(q.x, q.y, q.z); }
 				}
 				__syncthreads();
-				if (!done) {
-					const unsigned pos0 = s0 + c0 + b0;
-					for (int l0 = 0; l0 < nl; l0 += EVAL_U) {
-						float al[EVAL_U];
-						int jj[EVAL_U];
-#pragma unroll
-						for (int u = 0; u < EVAL_U; u++) { // independent evaluations: ILP
-							al[u] = 0.f;
-							jj[u] = 0;
-							if (l0 + u < nl) {
-								const int j = slist[warp][l0 + u];
-								jj[u] = j;
-								const float4 ex = sex[j];
-								const unsigned yp = __float_as_uint(ex.z);
-								const float4 a = sq0[j], b = sq1[j], c = sq2[j], d = sq3[j];
-								float dx, dy, ex_, ey_, ez_, du1, du2, G = 0.f;
-								const bool ok = lgs_pair_eval(ray, b.x, b.y, b.z, c.x, c.y, c.z, d.x, d.y, d.z,
-											      ex.x, ex.y, a.x, a.y, a.z, dx, dy, ex_, ey_, ez_,
-											      du1, du2, G);
-								const float alpha = fminf(0.99f, __fmul_rn(a.w, G));
-								const bool in_rows = py >= (int)(yp & 0xffffu) && py < (int)(yp >> 16);
-								// same skip rules as the reference: power > 0, alpha < 1/255
-								al[u] = (ok && in_rows && !(alpha < 1.0f / 255.0f)) ? alpha : 0.f;
-							}
+				// evaluate: task = (pixel group, entry group); lane = entry, loop over the group's live pixels
+				for (int task = warp; task < C::NTASK; task += NW) {
+					const int pg = task % NPG, eg = task / NPG;
+					unsigned lv = slive[pg];
+					if (eg * 32 >= bn || lv == 0) {
+						if (lane == 0) smask[pg * NEG + eg] = 0;
+						continue;
+					}
+					const int j = eg * 32 + lane;
+					const bool valid = j < bn;
+					const int jj = valid ? j : 0;
+					const float4 a = sq[jj], b = sq[B + jj], c = sq[2 * B + jj], d = sq[3 * B + jj];
+					const float2 uu = su[jj];
+					const unsigned yp = syp[jj];
+					const int ya = (int)(yp & 0xffffu), yb = (int)(yp >> 16);
+					const int row0 = rg * RB + 2 * pg;
+					// rows of this group the entry's rect covers (getRect_lidar's y range, aux.h:80-92)
+					const bool r0 = valid && row0 >= ya && row0 < yb, r1 = valid && row0 + 1 >= ya && row0 + 1 < yb;
+					float *trow = tile + (size_t)(pg * B + j) * LD;
+					const float4 *rays = sray + pg * 32;
+					bool any = false;
+					while (lv) {
+						const int p = __ffs(lv) - 1;
+						lv &= lv - 1;
+						const float4 rr = rays[p];
+						float alpha = 0.f;
+						if ((p < 16) ? r0 : r1) {
+							const PixelRay ray = {rr.x, rr.y, rr.z};
+							float dx, dy, ex_, ey_, ez_, du1, du2, G = 0.f;
+							const bool ok = lgs_pair_eval(ray, b.x, b.y, b.z, c.x, c.y, c.z, d.x, d.y, d.z, uu.x, uu.y,
+										      a.x, a.y, a.z, dx, dy, ex_, ey_, ez_, du1, du2, G);
+							const float al = fminf(0.99f, __fmul_rn(a.w, G));
+							// same skip rules as the reference: power > 0, alpha < 1/255
+							alpha = (ok && !(al < 1.0f / 255.0f)) ? al : 0.f;
 						}
+						if (valid) trow[p] = alpha;
+						any |= alpha != 0.f;
+					}
+					const unsigned m32 = __ballot_sync(0xffffffffu, any);
+					if (lane == 0) smask[pg * NEG + eg] = m32;
+				}
+				__syncthreads();
+				// blend: lane = pixel, serial over the entries that touch this group
+				if (blender && !__all_sync(0xffffffffu, done)) {
+					const unsigned pos0 = s0 + c0 + b0;
+					const float *tcol = tile + (size_t)(warp * B) * LD + lane;
 #pragma unroll
-						for (int u = 0; u < EVAL_U; u++) { // the only serial part: T
-							if (al[u] != 0.f && !done) {
-								const float alpha = al[u];
+					for (int eg = 0; eg < NEG; eg++) {
+						unsigned mw = smask[warp * NEG + eg];
+						while (mw) {
+							const int j = eg * 32 + __ffs(mw) - 1;
+							mw &= mw - 1;
+							const float alpha = tcol[(size_t)j * LD];
+							const float4 f = sfeat[j];
+							if (alpha != 0.f && !done) {
 								const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
 								if (test_T < 0.0001f) {
 									done = true;
 								} else {
-									const int j = jj[u];
-									C0 = __fmaf_rn(T, __fmul_rn(alpha, sq2[j].w), C0);
-									C1 = __fmaf_rn(T, __fmul_rn(alpha, sq3[j].w), C1);
-									D = __fmaf_rn(T, __fmul_rn(alpha, sq1[j].w), D);
+									C0 = __fmaf_rn(T, __fmul_rn(alpha, f.x), C0);
+									C1 = __fmaf_rn(T, __fmul_rn(alpha, f.y), C1);
+									D = __fmaf_rn(T, __fmul_rn(alpha, f.z), D);
 									T = test_T;
 									last = pos0 + j + 1;
 								}
 							}
 						}
-						if (done) break;
 					}
+					const unsigned lv = __ballot_sync(0xffffffffu, !done);
+					if (lane == 0) slive[warp] = lv;
 				}
-				if (__syncthreads_count(done) == NT) { all_done = true; break; }
 			}
 			if (all_done && !sort_all) break;
 		}
@@ -269,11 +341,27 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 		const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
 		final_T[pix] = T;
 		n_contrib[pix] = last;
+		fin[pix] = make_float4(C0, C1, D, 0.f);
 		out_color[pix] = __fmaf_rn(bg[0], T, C0);
 		out_color[HW + pix] = __fmaf_rn(bg[1], T, C1);
 		out_depth[pix] = D;
 		out_occ[pix] = __fsub_rn(1.0f, T);
 	}
+}
+
+template <int RB>
+void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries, const float *bg,
+		const float *beams, float *out_color, float *out_depth, float *out_occ, int sort_all, cudaStream_t st)
+{
+	using C = FwdCfg<RB>;
+	static bool configured = false;
+	if (!configured) {
+		cudaFuncSetAttribute(render_fwd_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+		configured = true;
+	}
+	render_fwd_kernel<RB><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, gp.order, entries, bg, beams,
+								 ip.final_T, ip.n_contrib, ip.sorted_end, ip.fin, out_color,
+								 out_depth, out_occ, sort_all);
 }
 
 } // namespace
@@ -282,16 +370,11 @@ void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePt
 			   const float *bg, const float *beams, float *out_color, float *out_depth, float *out_occ,
 			   int sort_all, cudaStream_t st)
 {
-#define LAUNCH(RB_)                                                                                              \
-	render_fwd_kernel<RB_><<<g.nbins, (RB_ >= 2 ? 16 * RB_ : 32), 0, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, bg, beams,    \
-							      ip.final_T, ip.n_contrib, ip.sorted_end, out_color,    \
-							      out_depth, out_occ, sort_all)
 	switch (g.RB) {
-	case 1: LAUNCH(1); break;
-	case 2: LAUNCH(2); break;
-	case 4: LAUNCH(4); break;
-	case 8: LAUNCH(8); break;
-	default: LAUNCH(16); break;
+	case 1: launch_fwd<1>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, st); break;
+	case 2: launch_fwd<2>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, st); break;
+	case 4: launch_fwd<4>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, st); break;
+	case 8: launch_fwd<8>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, st); break;
+	default: launch_fwd<16>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, st); break;
 	}
-#undef LAUNCH
 }
