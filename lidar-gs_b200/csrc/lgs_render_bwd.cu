@@ -26,22 +26,53 @@ template <int RB> struct BwdCfg {
 	static constexpr int NTASK = NPG * NEG;
 	static constexpr int NW = NTASK < 8 ? NTASK : 8;
 	static constexpr int NT = NW * 32;
-	static constexpr size_t TILE = 4 * (size_t)NPG * LGS_BATCH * LGS_TILE_LD;
-	static constexpr size_t O_Q = 0;                                  // 4 x float4[BATCH] record quarters
-	static constexpr size_t O_FEAT = O_Q + 4 * 16 * LGS_BATCH;        // float4 (f0, f1, depth, -)
-	static constexpr size_t O_RAY = O_FEAT + 16 * LGS_BATCH;          // float4 ray per pixel
-	static constexpr size_t O_G = O_RAY + 16 * 32 * NPG;              // float4 (g_color0, g_color1, g_depth, -) per pixel
+	static constexpr size_t TILE = 4 * (size_t)NPG * 32 * LGS_TILE_LD;    // [group][pixel][LGS_TILE_LD]
+	static constexpr int STAGE = 6 * 16 * LGS_BATCH + 8 * LGS_BATCH;      // 4 record quarters, feat, u, yp, id
+	static constexpr size_t O_STAGE = 0;                                  // 2 staging buffers (double buffered)
+	static constexpr size_t O_RAY = O_STAGE + 2 * STAGE;                  // float4 ray per pixel
+	static constexpr size_t O_G = O_RAY + 16 * 32 * NPG;                  // float4 (g_color0, g_color1, g_depth, -) per pixel
 	static constexpr size_t O_TA = O_G + 16 * 32 * NPG;
 	static constexpr size_t O_TB = O_TA + TILE;
-	static constexpr size_t O_U = O_TB + TILE;                        // float2 (|u1|^2, |u2|^2)
-	static constexpr size_t O_YP = O_U + 8 * LGS_BATCH;
-	static constexpr size_t O_ID = O_YP + 4 * LGS_BATCH;
-	static constexpr size_t O_LAST = O_ID + 4 * LGS_BATCH;            // last contributor per pixel
+	static constexpr size_t O_LAST = O_TB + TILE;                         // last contributor per pixel
 	static constexpr size_t O_MASK = O_LAST + 4 * 32 * NPG;
 	static constexpr size_t O_LIVE = O_MASK + 4 * NPG * NEG;
-	static constexpr size_t O_MAX = O_LIVE + 4 * NPG;
+	static constexpr size_t O_MAX = O_LIVE + 2 * 4 * NPG;                // slive is double buffered by batch parity
 	static constexpr size_t BYTES = O_MAX + 16;
 };
+
+struct BStage {
+	float4 *q;     // q[part * BATCH + j]
+	float4 *feat;  // (feature0, feature1, depth, -)
+	float4 *u;     // (|u1|^2, |u2|^2, refined 1/|u1|^2, refined 1/|u2|^2)
+	unsigned *yp;  // y0 | y1 << 16
+	unsigned *id;  // Gaussian index
+	__device__ __forceinline__ BStage(unsigned char *base)
+	{
+		q = reinterpret_cast<float4 *>(base);
+		feat = q + 4 * LGS_BATCH;
+		u = feat + LGS_BATCH;
+		yp = reinterpret_cast<unsigned *>(u + LGS_BATCH);
+		id = yp + LGS_BATCH;
+	}
+};
+
+__device__ __forceinline__ void bstage_batch(const BStage &st, const float4 *__restrict__ rec, const uint4 *__restrict__ ent,
+					     int bn, int t, int nthreads)
+{
+	for (int i = t; i < 4 * bn; i += nthreads) {
+		const int j = i >> 2, part = i & 3;
+		const uint4 e = ent[j];
+		const float4 q = rec[4 * (size_t)e.y + part];
+		st.q[part * LGS_BATCH + j] = q;
+		if (part == 0) { st.yp[j] = e.z; st.id[j] = e.y; }
+		else if (part == 1) st.feat[j].z = q.w;
+		else {
+			const float uu = lgs_dot_self(q.x, q.y, q.z), r = lgs_div_prep(uu);
+			if (part == 2) { st.feat[j].x = q.w; st.u[j].x = uu; st.u[j].z = r; }
+			else { st.feat[j].y = q.w; st.u[j].y = uu; st.u[j].w = r; }
+		}
+	}
+}
 
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
 {
@@ -58,16 +89,12 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 {
 	using C = BwdCfg<RB>;
 	constexpr int NT = C::NT, NW = C::NW, NPG = C::NPG, NEG = C::NEG, B = LGS_BATCH, LD = LGS_TILE_LD;
+	constexpr bool OVERLAP = NW > NPG;
 	extern __shared__ __align__(16) unsigned char smem[];
-	float4 *sq = reinterpret_cast<float4 *>(smem + C::O_Q);
-	float4 *sfeat = reinterpret_cast<float4 *>(smem + C::O_FEAT);
 	float4 *sray = reinterpret_cast<float4 *>(smem + C::O_RAY);
 	float4 *sg = reinterpret_cast<float4 *>(smem + C::O_G);
 	float *tileA = reinterpret_cast<float *>(smem + C::O_TA);
 	float *tileB = reinterpret_cast<float *>(smem + C::O_TB);
-	float2 *su = reinterpret_cast<float2 *>(smem + C::O_U);
-	unsigned *syp = reinterpret_cast<unsigned *>(smem + C::O_YP);
-	unsigned *sid = reinterpret_cast<unsigned *>(smem + C::O_ID);
 	unsigned *slast = reinterpret_cast<unsigned *>(smem + C::O_LAST);
 	unsigned *smask = reinterpret_cast<unsigned *>(smem + C::O_MASK);
 	unsigned *slive = reinterpret_cast<unsigned *>(smem + C::O_LIVE);
@@ -84,14 +111,14 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 	const bool blender = warp < NPG;
 	const bool inside = blender && px < g.W && py < g.H && 2 * warp + (lane >> 4) < RB;
 	float T = 1.f, S0 = 0.f, S1 = 0.f, SD = 0.f;
-	float Tf = 0.f, C0f = 0.f, C1f = 0.f, Df = 0.f, g0 = 0.f, g1 = 0.f, gd = 0.f, kocc = 0.f;
+	float C0f = 0.f, C1f = 0.f, Df = 0.f, g0 = 0.f, g1 = 0.f, gd = 0.f, kocc = 0.f;
 	unsigned lastc = 0;
 	if (blender) {
 		PixelRay ray = {0.f, 0.f, 0.f};
 		if (inside) {
 			const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
 			ray = lgs_pixel_ray(px, py, g.W, g.H, beams);
-			Tf = final_T[pix];
+			const float Tf = final_T[pix];
 			lastc = n_contrib[pix];
 			const float4 f = fin[pix];
 			C0f = f.x; C1f = f.y; Df = f.z;
@@ -111,31 +138,25 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 	}
 	__syncthreads();
 	const unsigned maxc = smax[0]; // deepest contributor of the bin: nothing behind it is replayed
+	if (maxc == 0) return;
 
-	for (unsigned lo = 0; lo < maxc; lo += B) {
+	bstage_batch(BStage(smem + C::O_STAGE), rec, entries + base, (int)min((unsigned)B, maxc), tid, NT);
+	int ib = 0;
+	for (unsigned lo = 0; lo < maxc; lo += B, ib++) {
 		const int bn = (int)min((unsigned)B, maxc - lo);
-		__syncthreads(); // previous batch fully consumed
-		for (int i = tid; i < 4 * bn; i += NT) {
-			const int j = i >> 2, part = i & 3;
-			const uint4 e = entries[base + lo + j];
-			const float4 q = rec[4 * (size_t)e.y + part];
-			sq[part * B + j] = q;
-			if (part == 0) { syp[j] = e.z; sid[j] = e.y; }
-			else if (part == 1) sfeat[j].z = q.w;
-			else if (part == 2) { sfeat[j].x = q.w; su[j].x = lgs_dot_self(q.x, q.y, q.z); }
-			else { sfeat[j].y = q.w; su[j].y = lgs_dot_self(q.x, q.y, q.z); }
-		}
+		const BStage st(smem + C::O_STAGE + (ib & 1) * C::STAGE);
 		const bool lane_live = lastc > lo;
+		unsigned *live = slive + (ib & 1) * NPG; // other parity: warps still in the previous batch's gradient phase read theirs
 		if (blender) {
 			const unsigned lv = __ballot_sync(0xffffffffu, lane_live);
-			if (lane == 0) slive[warp] = lv;
+			if (lane == 0) live[warp] = lv;
 		}
-		__syncthreads();
+		__syncthreads(); // batch staged, live set; previous batch's gradients done (tiles free)
 
 		// ---- 1: evaluate alpha, lanes = entries ----
 		for (int task = warp; task < C::NTASK; task += NW) {
 			const int pg = task % NPG, eg = task / NPG;
-			unsigned lv = slive[pg];
+			unsigned lv = live[pg];
 			if (eg * 32 >= bn || lv == 0) {
 				if (lane == 0) smask[pg * NEG + eg] = 0;
 				continue;
@@ -143,68 +164,78 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			const int j = eg * 32 + lane;
 			const bool valid = j < bn;
 			const int jj = valid ? j : 0;
-			const float4 a = sq[jj], b = sq[B + jj], c = sq[2 * B + jj], d = sq[3 * B + jj];
-			const float2 uu = su[jj];
-			const unsigned yp = syp[jj];
+			const float4 q0 = st.q[jj], q1 = st.q[B + jj], q2 = st.q[2 * B + jj], q3 = st.q[3 * B + jj];
+			const float4 uu = st.u[jj];
+			const unsigned yp = st.yp[jj];
 			const int ya = (int)(yp & 0xffffu), yb = (int)(yp >> 16);
 			const int row0 = rg * RB + 2 * pg;
-			const bool r0 = valid && row0 >= ya && row0 < yb, r1 = valid && row0 + 1 >= ya && row0 + 1 < yb;
-			float *trow = tileA + (size_t)(pg * B + j) * LD;
+			const unsigned rsel = ((valid && row0 >= ya && row0 < yb) ? 1u : 0u) |
+					      ((valid && row0 + 1 >= ya && row0 + 1 < yb) ? 2u : 0u);
+			float *tcol = tileA + (size_t)(pg * 32) * LD + j;
 			const float4 *rays = sray + pg * 32;
 			const unsigned *lasts = slast + pg * 32;
 			const unsigned pos = lo + (unsigned)j;
-			bool any = false;
+			float amax = 0.f;
 			while (lv) {
 				const int p = __ffs(lv) - 1;
 				lv &= lv - 1;
 				const float4 rr = rays[p];
 				float alpha = 0.f;
-				if (((p < 16) ? r0 : r1) && pos < lasts[p]) {
-					const PixelRay ray = {rr.x, rr.y, rr.z};
-					float dx, dy, ex_, ey_, ez_, du1, du2, G = 0.f;
-					const bool ok = lgs_pair_eval(ray, b.x, b.y, b.z, c.x, c.y, c.z, d.x, d.y, d.z, uu.x, uu.y, a.x, a.y,
-								      a.z, dx, dy, ex_, ey_, ez_, du1, du2, G);
-					const float al = fminf(0.99f, __fmul_rn(a.w, G));
-					alpha = (ok && !(al < 1.0f / 255.0f)) ? al : 0.f;
-				}
-				if (valid) trow[p] = alpha;
-				any |= alpha != 0.f;
+				if (((rsel >> (p >> 4)) & 1u) && pos < lasts[p]) alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, q0, q1, q2, q3, uu);
+				tcol[p * LD] = alpha;
+				amax = fmaxf(amax, alpha);
 			}
-			const unsigned m32 = __ballot_sync(0xffffffffu, any);
+			const unsigned m32 = __ballot_sync(0xffffffffu, amax != 0.f);
 			if (lane == 0) smask[pg * NEG + eg] = m32;
 		}
 		__syncthreads();
 
-		// ---- 2: scan, lanes = pixels ----
-		if (blender && slive[warp] != 0) {
-			float *ta = tileA + (size_t)(warp * B) * LD + lane;
-			float *tb = tileB + (size_t)(warp * B) * LD + lane;
+		// ---- 2: scan, lanes = pixels (spare warps prefetch the next batch meanwhile) ----
+		if (blender) {
+			if (live[warp] != 0) {
+				float *ta = tileA + (size_t)(warp * 32 + lane) * LD;
+				float *tb = tileB + (size_t)(warp * 32 + lane) * LD;
 #pragma unroll
-			for (int eg = 0; eg < NEG; eg++) {
-				unsigned mw = smask[warp * NEG + eg];
-				while (mw) {
-					const int j = eg * 32 + __ffs(mw) - 1;
-					mw &= mw - 1;
-					const float alpha = lane_live ? ta[(size_t)j * LD] : 0.f;
-					const float4 f = sfeat[j];
-					float w = 0.f, dLda = 0.f;
-					if (alpha != 0.f) {
-						const float om = __fsub_rn(1.0f, alpha);
-						const float r = __frcp_rn(om);
-						w = alpha * T;
-						// forward's own accumulation order: S_i == forward's running C at this entry
-						S0 = __fmaf_rn(T, __fmul_rn(alpha, f.x), S0);
-						S1 = __fmaf_rn(T, __fmul_rn(alpha, f.y), S1);
-						SD = __fmaf_rn(T, __fmul_rn(alpha, f.z), SD);
-						const float q = f.x * g0 + f.y * g1 + f.z * gd;
-						const float rem = (C0f - S0) * g0 + (C1f - S1) * g1 + (Df - SD) * gd;
-						dLda = T * q - (rem - kocc) * r;
-						T = __fmul_rn(T, om);
+				for (int eg = 0; eg < NEG; eg++) {
+					const unsigned mw = smask[warp * NEG + eg];
+					for (int j0 = 0; j0 < 32; j0 += 4) {
+						const unsigned nib = (mw >> j0) & 0xfu;
+						if (nib == 0) continue;
+						const int jb = eg * 32 + j0;
+						float4 a4 = *reinterpret_cast<const float4 *>(ta + jb);
+						if (!lane_live) a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+						const float4 f0 = st.feat[jb], f1 = st.feat[jb + 1], f2 = st.feat[jb + 2], f3 = st.feat[jb + 3];
+						float4 dl = make_float4(0.f, 0.f, 0.f, 0.f), w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#define LGS_SCAN1(al_, f_, bit_, dl_, w_)                                                                  \
+	if ((nib & (1u << bit_)) && al_ != 0.f) {                                                          \
+		const float om = __fsub_rn(1.0f, al_);                                                     \
+		const float r = __fdividef(1.0f, om);                                                      \
+		w_ = al_ * T;                                                                              \
+		S0 = __fmaf_rn(T, __fmul_rn(al_, f_.x), S0); /* forward's own accumulation order */        \
+		S1 = __fmaf_rn(T, __fmul_rn(al_, f_.y), S1);                                               \
+		SD = __fmaf_rn(T, __fmul_rn(al_, f_.z), SD);                                               \
+		const float q = f_.x * g0 + f_.y * g1 + f_.z * gd;                                         \
+		const float rem = (C0f - S0) * g0 + (C1f - S1) * g1 + (Df - SD) * gd;                      \
+		dl_ = T * q - (rem - kocc) * r;                                                            \
+		T = __fmul_rn(T, om);                                                                      \
+	}
+						LGS_SCAN1(a4.x, f0, 0, dl.x, w4.x)
+						LGS_SCAN1(a4.y, f1, 1, dl.y, w4.y)
+						LGS_SCAN1(a4.z, f2, 2, dl.z, w4.z)
+						LGS_SCAN1(a4.w, f3, 3, dl.w, w4.w)
+#undef LGS_SCAN1
+						*reinterpret_cast<float4 *>(ta + jb) = dl;
+						*reinterpret_cast<float4 *>(tb + jb) = w4;
 					}
-					ta[(size_t)j * LD] = dLda;
-					tb[(size_t)j * LD] = w;
 				}
 			}
+			if (!OVERLAP && lo + B < maxc) {
+				bstage_batch(BStage(smem + C::O_STAGE + ((ib + 1) & 1) * C::STAGE), rec, entries + base + lo + B,
+					     (int)min((unsigned)B, maxc - lo - B), tid, NT);
+			}
+		} else if (lo + B < maxc) {
+			bstage_batch(BStage(smem + C::O_STAGE + ((ib + 1) & 1) * C::STAGE), rec, entries + base + lo + B,
+				     (int)min((unsigned)B, maxc - lo - B), tid - NPG * 32, NT - NPG * 32);
 		}
 		__syncthreads();
 
@@ -213,23 +244,23 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			const int pg = task % NPG, eg = task / NPG;
 			const unsigned m32 = smask[pg * NEG + eg];
 			if (!((m32 >> lane) & 1u)) continue;
-			unsigned lv = slive[pg];
+			unsigned lv = live[pg];
 			const int j = eg * 32 + lane;
-			const float4 a = sq[j], b = sq[B + j], c = sq[2 * B + j], d = sq[3 * B + j];
-			const float2 uu = su[j];
-			const float r11 = 1.f / uu.x, r22 = 1.f / uu.y;
+			const float4 a = st.q[j], b = st.q[B + j], c = st.q[2 * B + j], d = st.q[3 * B + j];
+			const float4 uu = st.u[j];
+			const float r11 = uu.z, r22 = uu.w;
 			const float ab = (c.x * d.x + c.y * d.y + c.z * d.z) * r11 * r22; // (u1/|u1|^2) . (u2/|u2|^2)
-			const float *ta = tileA + (size_t)(pg * B + j) * LD;
-			const float *tb = tileB + (size_t)(pg * B + j) * LD;
+			const float *ta = tileA + (size_t)(pg * 32) * LD + j;
+			const float *tb = tileB + (size_t)(pg * 32) * LD + j;
 			const float4 *rays = sray + pg * 32, *gs = sg + pg * 32;
 			float sKx = 0.f, sKy = 0.f, sM = 0.f, aXx = 0.f, aXy = 0.f, aXz = 0.f, aXu = 0.f, aYx = 0.f, aYy = 0.f,
 			      aYz = 0.f, aYu = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, opa = 0.f, col0 = 0.f, col1 = 0.f, dep = 0.f;
 			while (lv) {
 				const int p = __ffs(lv) - 1;
 				lv &= lv - 1;
-				const float w = tb[p];
+				const float w = tb[p * LD];
 				if (w == 0.f) continue;
-				const float dLda = ta[p];
+				const float dLda = ta[p * LD];
 				const float4 rr = rays[p], gg = gs[p];
 				const float ddx = b.x - rr.x, ddy = b.y - rr.y, ddz = b.z - rr.z;
 				const float du1 = ddx * c.x + ddy * c.y + ddz * c.z, du2 = ddx * d.x + ddy * d.y + ddz * d.z;
@@ -248,7 +279,7 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 				opa += G * dLda;
 				col0 += w * gg.x; col1 += w * gg.y; dep += w * gg.z;
 			}
-			float *row = grad + (size_t)sid[j] * LGS_GRAD_STRIDE;
+			float *row = grad + (size_t)st.id[j] * LGS_GRAD_STRIDE;
 			const float i11 = r11 * r11, i22 = r22 * r22;
 			// component order: G_M2X.. in lgs_common.cuh
 			red_add_v4(row + 0, sKx, sKy, sM, -0.5f * cA);

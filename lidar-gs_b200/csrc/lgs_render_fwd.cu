@@ -114,28 +114,75 @@ __device__ __forceinline__ void rank_sort_small(const unsigned long long *__rest
 	}
 }
 
+// one entry per thread (n <= NT): the rank loop without the second, wasted, comparison stream
+template <int NT>
+__device__ __forceinline__ void rank_sort_one(const unsigned long long *__restrict__ key, const unsigned *__restrict__ val,
+					      unsigned long long *__restrict__ okey, unsigned *__restrict__ oval, int n, int tid)
+{
+	if (tid < n) {
+		const unsigned long long k0 = key[tid];
+		int r0 = 0;
+#pragma unroll 8
+		for (int j = 0; j < n; j++) r0 += key[j] < k0;
+		okey[r0] = k0;
+		oval[r0] = val[tid];
+	}
+}
+
 template <int RB> struct FwdCfg {
 	static constexpr int NPG = RB >= 2 ? RB / 2 : 1;     // 32-pixel groups (2 rows x 16 columns)
 	static constexpr int NEG = LGS_BATCH / 32;            // 32-entry groups per batch
 	static constexpr int NTASK = NPG * NEG;               // evaluate tasks per batch
 	static constexpr int NW = NTASK < 8 ? NTASK : 8;      // warps per CTA (>= NPG for every RB)
 	static constexpr int NT = NW * 32;
+	static constexpr int STAGE = 6 * 16 * LGS_BATCH + 4 * LGS_BATCH; // one staging buffer: 4 record quarters, feat, u, yp
 	// dynamic shared memory carve-up (bytes)
 	static constexpr size_t O_KEYA = 0;
 	static constexpr size_t O_KEYB = O_KEYA + 8 * LGS_SEG_CAP;
-	static constexpr size_t O_Q = O_KEYB + 8 * RANK_SORT_MAX;            // 4 x float4[BATCH] record quarters
-	static constexpr size_t O_FEAT = O_Q + 4 * 16 * LGS_BATCH;            // float4 (f0, f1, depth, -)
-	static constexpr size_t O_RAY = O_FEAT + 16 * LGS_BATCH;              // float4 per pixel of every group
-	static constexpr size_t O_TILE = O_RAY + 16 * 32 * NPG;               // alpha tile
-	static constexpr size_t O_VALA = O_TILE + 4 * (size_t)NPG * LGS_BATCH * LGS_TILE_LD;
+	static constexpr size_t O_STAGE = O_KEYB + 8 * RANK_SORT_MAX;        // 2 staging buffers (double buffered)
+	static constexpr size_t O_RAY = O_STAGE + 2 * STAGE;                  // float4 per pixel of every group
+	static constexpr size_t O_TILE = O_RAY + 16 * 32 * NPG;               // alpha tile [group][pixel][LGS_TILE_LD]
+	static constexpr size_t O_VALA = O_TILE + 4 * (size_t)NPG * 32 * LGS_TILE_LD;
 	static constexpr size_t O_VALB = O_VALA + 4 * LGS_SEG_CAP;
-	static constexpr size_t O_U = O_VALB + 4 * RANK_SORT_MAX;             // float2 (|u1|^2, |u2|^2)
-	static constexpr size_t O_YP = O_U + 8 * LGS_BATCH;                   // y0 | y1 << 16
-	static constexpr size_t O_MASK = O_YP + 4 * LGS_BATCH;                // per (group, entry group): entries with alpha != 0
+	static constexpr size_t O_MASK = O_VALB + 4 * RANK_SORT_MAX;          // per (group, entry group): entries with alpha != 0
 	static constexpr size_t O_LIVE = O_MASK + 4 * NPG * NEG;              // per group: pixels not yet terminated
 	static constexpr size_t O_LOC = O_LIVE + 4 * NPG;
 	static constexpr size_t BYTES = O_LOC + 4 * (LGS_NB + 1);
 };
+
+// views into one staging buffer
+struct Stage {
+	float4 *q;     // q[part * BATCH + j]: the four quarters of entry j's record
+	float4 *feat;  // (feature0, feature1, depth, -)
+	float4 *u;     // (|u1|^2, |u2|^2, refined 1/|u1|^2, refined 1/|u2|^2)
+	unsigned *yp;  // y0 | y1 << 16
+	__device__ __forceinline__ Stage(unsigned char *base)
+	{
+		q = reinterpret_cast<float4 *>(base);
+		feat = q + 4 * LGS_BATCH;
+		u = feat + LGS_BATCH;
+		yp = reinterpret_cast<unsigned *>(u + LGS_BATCH);
+	}
+};
+
+// gather the records of entries [b0, b0 + bn) of the sorted chunk into a staging buffer: one float4 per thread
+__device__ __forceinline__ void stage_batch(const Stage &st, const float4 *__restrict__ rec, const unsigned long long *skey,
+					    const unsigned *sval, int b0, int bn, int t, int nthreads)
+{
+	for (int i = t; i < 4 * bn; i += nthreads) {
+		const int j = i >> 2, part = i & 3;
+		const unsigned id = (unsigned)skey[b0 + j];
+		const float4 q = rec[4 * (size_t)id + part];
+		st.q[part * LGS_BATCH + j] = q;
+		if (part == 0) st.yp[j] = sval[b0 + j];
+		else if (part == 1) st.feat[j].z = q.w;
+		else {
+			const float uu = lgs_dot_self(q.x, q.y, q.z), r = lgs_div_prep(uu);
+			if (part == 2) { st.feat[j].x = q.w; st.u[j].x = uu; st.u[j].z = r; }
+			else { st.feat[j].y = q.w; st.u[j].y = uu; st.u[j].w = r; }
+		}
+	}
+}
 
 template <int RB>
 __global__ void __launch_bounds__(FwdCfg<RB>::NT)
@@ -148,17 +195,14 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 {
 	using C = FwdCfg<RB>;
 	constexpr int NT = C::NT, NW = C::NW, NPG = C::NPG, NEG = C::NEG, B = LGS_BATCH, LD = LGS_TILE_LD;
+	constexpr bool OVERLAP = NW > NPG; // spare warps prefetch the next batch while the blend warps composite
 	extern __shared__ __align__(16) unsigned char smem[];
 	unsigned long long *skeyA = reinterpret_cast<unsigned long long *>(smem + C::O_KEYA);
 	unsigned long long *skeyB = reinterpret_cast<unsigned long long *>(smem + C::O_KEYB);
-	float4 *sq = reinterpret_cast<float4 *>(smem + C::O_Q); // sq[part * B + j]
-	float4 *sfeat = reinterpret_cast<float4 *>(smem + C::O_FEAT);
 	float4 *sray = reinterpret_cast<float4 *>(smem + C::O_RAY);
 	float *tile = reinterpret_cast<float *>(smem + C::O_TILE);
 	unsigned *svalA = reinterpret_cast<unsigned *>(smem + C::O_VALA);
 	unsigned *svalB = reinterpret_cast<unsigned *>(smem + C::O_VALB);
-	float2 *su = reinterpret_cast<float2 *>(smem + C::O_U);
-	unsigned *syp = reinterpret_cast<unsigned *>(smem + C::O_YP);
 	unsigned *smask = reinterpret_cast<unsigned *>(smem + C::O_MASK);
 	unsigned *slive = reinterpret_cast<unsigned *>(smem + C::O_LIVE);
 	unsigned *sloc = reinterpret_cast<unsigned *>(smem + C::O_LOC);
@@ -174,7 +218,7 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 	const bool blender = warp < NPG;
 	const bool inside = blender && px < g.W && py < g.H && 2 * warp + (lane >> 4) < RB;
 	float T = 1.0f, C0 = 0.f, C1 = 0.f, D = 0.f;
-	unsigned last = 0;
+	unsigned last = 0, stop = 0; // stop: list position of the entry that terminated the pixel (diagnostic)
 	bool done = !inside;
 	if (blender) {
 		PixelRay ray = {0.f, 0.f, 0.f};
@@ -184,6 +228,7 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 		if (lane == 0) slive[warp] = lv;
 	}
 	bool all_done = false;
+	int nstaged = 0; // batches staged so far: selects the staging buffer
 	__syncthreads();
 
 	int k = 0;
@@ -224,7 +269,8 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			const unsigned *sval = svalA;
 			if (!oversized && m > 1) {
 				if (m <= RANK_SORT_MAX) {
-					rank_sort_small<NT>(skeyA, svalA, skeyB, svalB, m, tid);
+					if (m <= NT) rank_sort_one<NT>(skeyA, svalA, skeyB, svalB, m, tid);
+					else rank_sort_small<NT>(skeyA, svalA, skeyB, svalB, m, tid);
 					skey = skeyB;
 					sval = svalB;
 					__syncthreads();
@@ -237,28 +283,19 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 				}
 			}
 			if (all_done) continue; // sort_all mode: keep sorting, nothing left to blend
-			// ---- composite the m sorted entries in batches ----
+			// ---- composite the m sorted entries in batches (staging is double buffered) ----
+			stage_batch(Stage(smem + C::O_STAGE + (nstaged & 1) * C::STAGE), rec, skey, sval, 0, min(B, m), tid, NT);
+			nstaged++;
 			for (int b0 = 0; b0 < m; b0 += B) {
 				const int bn = min(B, m - b0);
-				__syncthreads(); // previous batch fully consumed; slive final
+				const Stage st(smem + C::O_STAGE + ((nstaged - 1) & 1) * C::STAGE);
+				__syncthreads(); // batch staged; previous batch blended (slive, tile free)
 				{
 					unsigned any_live = 0;
 #pragma unroll
 					for (int i = 0; i < NPG; i++) any_live |= slive[i];
 					if (any_live == 0) { all_done = true; break; }
 				}
-				// stage the batch: one float4 (a quarter record) per thread
-				for (int i = tid; i < 4 * bn; i += NT) {
-					const int j = i >> 2, part = i & 3;
-					const unsigned id = (unsigned)skey[b0 + j];
-					const float4 q = rec[4 * (size_t)id + part];
-					sq[part * B + j] = q;
-					if (part == 0) syp[j] = sval[b0 + j];
-					else if (part == 1) sfeat[j].z = q.w;
-					else if (part == 2) { sfeat[j].x = q.w; su[j].x = lgs_dot_self(q.x, q.y, q.z); }
-					else { sfeat[j].y = q.w; su[j].y = lgs_dot_self(q.x, q.y, q.z); }
-				}
-				__syncthreads();
 				// evaluate: task = (pixel group, entry group); lane = entry, loop over the group's live pixels
 				for (int task = warp; task < C::NTASK; task += NW) {
 					const int pg = task % NPG, eg = task / NPG;
@@ -270,66 +307,80 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 					const int j = eg * 32 + lane;
 					const bool valid = j < bn;
 					const int jj = valid ? j : 0;
-					const float4 a = sq[jj], b = sq[B + jj], c = sq[2 * B + jj], d = sq[3 * B + jj];
-					const float2 uu = su[jj];
-					const unsigned yp = syp[jj];
+					const float4 q0 = st.q[jj], q1 = st.q[B + jj], q2 = st.q[2 * B + jj], q3 = st.q[3 * B + jj];
+					const float4 uu = st.u[jj];
+					const unsigned yp = st.yp[jj];
 					const int ya = (int)(yp & 0xffffu), yb = (int)(yp >> 16);
 					const int row0 = rg * RB + 2 * pg;
-					// rows of this group the entry's rect covers (getRect_lidar's y range, aux.h:80-92)
-					const bool r0 = valid && row0 >= ya && row0 < yb, r1 = valid && row0 + 1 >= ya && row0 + 1 < yb;
-					float *trow = tile + (size_t)(pg * B + j) * LD;
+					// rows of this group the entry's rect covers (getRect_lidar's y range, aux.h:80-92):
+					// bit p>>4 of rsel says whether pixel p's row is inside
+					const unsigned rsel = ((valid && row0 >= ya && row0 < yb) ? 1u : 0u) |
+							      ((valid && row0 + 1 >= ya && row0 + 1 < yb) ? 2u : 0u);
+					float *tcol = tile + (size_t)(pg * 32) * LD + j;
 					const float4 *rays = sray + pg * 32;
-					bool any = false;
+					float amax = 0.f;
 					while (lv) {
 						const int p = __ffs(lv) - 1;
 						lv &= lv - 1;
 						const float4 rr = rays[p];
 						float alpha = 0.f;
-						if ((p < 16) ? r0 : r1) {
-							const PixelRay ray = {rr.x, rr.y, rr.z};
-							float dx, dy, ex_, ey_, ez_, du1, du2, G = 0.f;
-							const bool ok = lgs_pair_eval(ray, b.x, b.y, b.z, c.x, c.y, c.z, d.x, d.y, d.z, uu.x, uu.y,
-										      a.x, a.y, a.z, dx, dy, ex_, ey_, ez_, du1, du2, G);
-							const float al = fminf(0.99f, __fmul_rn(a.w, G));
-							// same skip rules as the reference: power > 0, alpha < 1/255
-							alpha = (ok && !(al < 1.0f / 255.0f)) ? al : 0.f;
-						}
-						if (valid) trow[p] = alpha;
-						any |= alpha != 0.f;
+						if ((rsel >> (p >> 4)) & 1u) alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, q0, q1, q2, q3, uu);
+						tcol[p * LD] = alpha;
+						amax = fmaxf(amax, alpha);
 					}
-					const unsigned m32 = __ballot_sync(0xffffffffu, any);
+					const unsigned m32 = __ballot_sync(0xffffffffu, amax != 0.f);
 					if (lane == 0) smask[pg * NEG + eg] = m32;
 				}
 				__syncthreads();
-				// blend: lane = pixel, serial over the entries that touch this group
-				if (blender && !__all_sync(0xffffffffu, done)) {
-					const unsigned pos0 = s0 + c0 + b0;
-					const float *tcol = tile + (size_t)(warp * B) * LD + lane;
+				if (blender) {
+					// blend: lane = pixel, serial over the entries that touch this group, four at a time
+					if (!__all_sync(0xffffffffu, done)) {
+						const unsigned pos0 = s0 + c0 + b0;
+						const float *trow = tile + (size_t)(warp * 32 + lane) * LD;
 #pragma unroll
-					for (int eg = 0; eg < NEG; eg++) {
-						unsigned mw = smask[warp * NEG + eg];
-						while (mw) {
-							const int j = eg * 32 + __ffs(mw) - 1;
-							mw &= mw - 1;
-							const float alpha = tcol[(size_t)j * LD];
-							const float4 f = sfeat[j];
-							if (alpha != 0.f && !done) {
-								const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-								if (test_T < 0.0001f) {
-									done = true;
-								} else {
-									C0 = __fmaf_rn(T, __fmul_rn(alpha, f.x), C0);
-									C1 = __fmaf_rn(T, __fmul_rn(alpha, f.y), C1);
-									D = __fmaf_rn(T, __fmul_rn(alpha, f.z), D);
-									T = test_T;
-									last = pos0 + j + 1;
-								}
+						for (int eg = 0; eg < NEG; eg++) {
+							const unsigned mw = smask[warp * NEG + eg];
+							for (int j0 = 0; j0 < 32; j0 += 4) {
+								const unsigned nib = (mw >> j0) & 0xfu;
+								if (nib == 0) continue;
+								const int jb = eg * 32 + j0;
+								const float4 a4 = *reinterpret_cast<const float4 *>(trow + jb);
+								const float4 f0 = st.feat[jb], f1 = st.feat[jb + 1], f2 = st.feat[jb + 2], f3 = st.feat[jb + 3];
+#define LGS_BLEND1(al_, f_, bit_)                                                                  \
+	if ((nib & (1u << bit_)) && al_ != 0.f && !done) {                                         \
+		const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al_));                           \
+		if (test_T < 0.0001f) {                                                            \
+			done = true;                                                               \
+			stop = pos0 + jb + bit_ + 1;                                               \
+		} else {                                                                           \
+			C0 = __fmaf_rn(T, __fmul_rn(al_, f_.x), C0);                               \
+			C1 = __fmaf_rn(T, __fmul_rn(al_, f_.y), C1);                               \
+			D = __fmaf_rn(T, __fmul_rn(al_, f_.z), D);                                 \
+			T = test_T;                                                                \
+			last = pos0 + jb + bit_ + 1;                                               \
+		}                                                                                  \
+	}
+								LGS_BLEND1(a4.x, f0, 0)
+								LGS_BLEND1(a4.y, f1, 1)
+								LGS_BLEND1(a4.z, f2, 2)
+								LGS_BLEND1(a4.w, f3, 3)
+#undef LGS_BLEND1
 							}
 						}
+						const unsigned lv = __ballot_sync(0xffffffffu, !done);
+						if (lane == 0) slive[warp] = lv;
 					}
-					const unsigned lv = __ballot_sync(0xffffffffu, !done);
-					if (lane == 0) slive[warp] = lv;
+					if (!OVERLAP && b0 + B < m) { // no spare warps: every warp stages after its blend
+						__syncthreads();
+						stage_batch(Stage(smem + C::O_STAGE + (nstaged & 1) * C::STAGE), rec, skey, sval, b0 + B,
+							    min(B, m - b0 - B), tid, NT);
+					}
+				} else if (b0 + B < m) {
+					// spare warps: prefetch the next batch into the other staging buffer meanwhile
+					stage_batch(Stage(smem + C::O_STAGE + (nstaged & 1) * C::STAGE), rec, skey, sval, b0 + B,
+						    min(B, m - b0 - B), tid - NPG * 32, NT - NPG * 32);
 				}
+				if (b0 + B < m) nstaged++;
 			}
 			if (all_done && !sort_all) break;
 		}
@@ -341,7 +392,7 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 		const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
 		final_T[pix] = T;
 		n_contrib[pix] = last;
-		fin[pix] = make_float4(C0, C1, D, 0.f);
+		fin[pix] = make_float4(C0, C1, D, __uint_as_float(stop));
 		out_color[pix] = __fmaf_rn(bg[0], T, C0);
 		out_color[HW + pix] = __fmaf_rn(bg[1], T, C1);
 		out_depth[pix] = D;
