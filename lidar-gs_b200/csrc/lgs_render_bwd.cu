@@ -23,8 +23,8 @@ namespace {
 template <int RB> struct BwdCfg {
 	static constexpr int NPG = RB >= 2 ? RB / 2 : 1;
 	static constexpr int NEG = LGS_BATCH / 32;
-	static constexpr int NTASK = NPG * NEG;
-	static constexpr int NW = NTASK < 8 ? NTASK : 8;
+	static constexpr int NTASK = NPG * NEG * 2; // (pixel group, entry group, row of the group)
+	static constexpr int NW = NTASK < 16 ? NTASK : 16;
 	static constexpr int NT = NW * 32;
 	static constexpr size_t TILE = 4 * (size_t)NPG * 32 * LGS_TILE_LD;    // [group][pixel][LGS_TILE_LD]
 	static constexpr int STAGE = 6 * 16 * LGS_BATCH + 8 * LGS_BATCH;      // 4 record quarters, feat, u, yp, id
@@ -35,7 +35,7 @@ template <int RB> struct BwdCfg {
 	static constexpr size_t O_TB = O_TA + TILE;
 	static constexpr size_t O_LAST = O_TB + TILE;                         // last contributor per pixel
 	static constexpr size_t O_MASK = O_LAST + 4 * 32 * NPG;
-	static constexpr size_t O_LIVE = O_MASK + 4 * NPG * NEG;
+	static constexpr size_t O_LIVE = O_MASK + 4 * NPG * NEG * 2;
 	static constexpr size_t O_MAX = O_LIVE + 2 * 4 * NPG;                // slive is double buffered by batch parity
 	static constexpr size_t BYTES = O_MAX + 16;
 };
@@ -80,7 +80,7 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 }
 
 template <int RB>
-__global__ void __launch_bounds__(BwdCfg<RB>::NT)
+__global__ void __launch_bounds__(BwdCfg<RB>::NT, BwdCfg<RB>::NT >= 512 ? 2 : 1)
 render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ binbase,
 		  const uint32_t *__restrict__ order, const uint4 *__restrict__ entries, const float *__restrict__ bg,
 		  const float *__restrict__ beams, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
@@ -153,27 +153,33 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 		}
 		__syncthreads(); // batch staged, live set; previous batch's gradients done (tiles free)
 
-		// ---- 1: evaluate alpha, lanes = entries ----
+		// ---- 1: evaluate alpha: task = (pixel group, entry group, row), lanes = entries ----
 		for (int task = warp; task < C::NTASK; task += NW) {
-			const int pg = task % NPG, eg = task / NPG;
-			unsigned lv = live[pg];
-			if (eg * 32 >= bn || lv == 0) {
-				if (lane == 0) smask[pg * NEG + eg] = 0;
-				continue;
-			}
+			const int pg = task % NPG, eg = (task / NPG) % NEG, h = task / (NPG * NEG);
+			unsigned lv = (live[pg] >> (16 * h)) & 0xffffu;
 			const int j = eg * 32 + lane;
 			const bool valid = j < bn;
 			const int jj = valid ? j : 0;
+			const unsigned yp = st.yp[jj];
+			const int row = rg * RB + 2 * pg + h;
+			const bool rowok = valid && row >= (int)(yp & 0xffffu) && row < (int)(yp >> 16);
+			if (eg * 32 >= bn || lv == 0 || !__any_sync(0xffffffffu, rowok)) {
+				if (lane == 0) smask[(pg * NEG + eg) * 2 + h] = 0;
+				if (eg * 32 < bn && lv != 0) {
+					float *tz = tileA + (size_t)(pg * 32 + 16 * h) * LD + j;
+					while (lv) {
+						const int p = __ffs(lv) - 1;
+						lv &= lv - 1;
+						tz[p * LD] = 0.f;
+					}
+				}
+				continue;
+			}
 			const float4 q0 = st.q[jj], q1 = st.q[B + jj], q2 = st.q[2 * B + jj], q3 = st.q[3 * B + jj];
 			const float4 uu = st.u[jj];
-			const unsigned yp = st.yp[jj];
-			const int ya = (int)(yp & 0xffffu), yb = (int)(yp >> 16);
-			const int row0 = rg * RB + 2 * pg;
-			const unsigned rsel = ((valid && row0 >= ya && row0 < yb) ? 1u : 0u) |
-					      ((valid && row0 + 1 >= ya && row0 + 1 < yb) ? 2u : 0u);
-			float *tcol = tileA + (size_t)(pg * 32) * LD + j;
-			const float4 *rays = sray + pg * 32;
-			const unsigned *lasts = slast + pg * 32;
+			float *tcol = tileA + (size_t)(pg * 32 + 16 * h) * LD + j;
+			const float4 *rays = sray + pg * 32 + 16 * h;
+			const unsigned *lasts = slast + pg * 32 + 16 * h;
 			const unsigned pos = lo + (unsigned)j;
 			float amax = 0.f;
 			while (lv) {
@@ -181,12 +187,12 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 				lv &= lv - 1;
 				const float4 rr = rays[p];
 				float alpha = 0.f;
-				if (((rsel >> (p >> 4)) & 1u) && pos < lasts[p]) alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, q0, q1, q2, q3, uu);
+				if (rowok && pos < lasts[p]) alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, q0, q1, q2, q3, uu);
 				tcol[p * LD] = alpha;
 				amax = fmaxf(amax, alpha);
 			}
 			const unsigned m32 = __ballot_sync(0xffffffffu, amax != 0.f);
-			if (lane == 0) smask[pg * NEG + eg] = m32;
+			if (lane == 0) smask[(pg * NEG + eg) * 2 + h] = m32;
 		}
 		__syncthreads();
 
@@ -197,7 +203,7 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 				float *tb = tileB + (size_t)(warp * 32 + lane) * LD;
 #pragma unroll
 				for (int eg = 0; eg < NEG; eg++) {
-					const unsigned mw = smask[warp * NEG + eg];
+					const unsigned mw = smask[(warp * NEG + eg) * 2] | smask[(warp * NEG + eg) * 2 + 1];
 					for (int j0 = 0; j0 < 32; j0 += 4) {
 						const unsigned nib = (mw >> j0) & 0xfu;
 						if (nib == 0) continue;
@@ -239,20 +245,20 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 		}
 		__syncthreads();
 
-		// ---- 3: gradients, lanes = entries, sums over pixels stay in registers ----
+		// ---- 3: gradients: same tasks, lanes = entries, sums over the row's pixels stay in registers ----
 		for (int task = warp; task < C::NTASK; task += NW) {
-			const int pg = task % NPG, eg = task / NPG;
-			const unsigned m32 = smask[pg * NEG + eg];
+			const int pg = task % NPG, eg = (task / NPG) % NEG, h = task / (NPG * NEG);
+			const unsigned m32 = smask[(pg * NEG + eg) * 2 + h]; // entries with a contribution in THIS row
 			if (!((m32 >> lane) & 1u)) continue;
-			unsigned lv = live[pg];
+			unsigned lv = (live[pg] >> (16 * h)) & 0xffffu;
 			const int j = eg * 32 + lane;
 			const float4 a = st.q[j], b = st.q[B + j], c = st.q[2 * B + j], d = st.q[3 * B + j];
 			const float4 uu = st.u[j];
 			const float r11 = uu.z, r22 = uu.w;
 			const float ab = (c.x * d.x + c.y * d.y + c.z * d.z) * r11 * r22; // (u1/|u1|^2) . (u2/|u2|^2)
-			const float *ta = tileA + (size_t)(pg * 32) * LD + j;
-			const float *tb = tileB + (size_t)(pg * 32) * LD + j;
-			const float4 *rays = sray + pg * 32, *gs = sg + pg * 32;
+			const float *ta = tileA + (size_t)(pg * 32 + 16 * h) * LD + j;
+			const float *tb = tileB + (size_t)(pg * 32 + 16 * h) * LD + j;
+			const float4 *rays = sray + pg * 32 + 16 * h, *gs = sg + pg * 32 + 16 * h;
 			float sKx = 0.f, sKy = 0.f, sM = 0.f, aXx = 0.f, aXy = 0.f, aXz = 0.f, aXu = 0.f, aYx = 0.f, aYy = 0.f,
 			      aYz = 0.f, aYu = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, opa = 0.f, col0 = 0.f, col1 = 0.f, dep = 0.f;
 			while (lv) {

@@ -114,16 +114,23 @@ __device__ __forceinline__ void rank_sort_small(const unsigned long long *__rest
 	}
 }
 
-// one entry per thread (n <= NT): the rank loop without the second, wasted, comparison stream
+// One entry per thread (n <= NT).  The segment is a run of whole depth buckets and buckets are monotone in
+// depth, so an entry only has to be ranked inside its own bucket: rank = bucket offset + #smaller keys there.
+// bloc[0 .. nb] are the list positions of the segment's bucket boundaries (bloc[0] = segment start).
 template <int NT>
-__device__ __forceinline__ void rank_sort_one(const unsigned long long *__restrict__ key, const unsigned *__restrict__ val,
-					      unsigned long long *__restrict__ okey, unsigned *__restrict__ oval, int n, int tid)
+__device__ __forceinline__ void rank_sort_buckets(const unsigned long long *__restrict__ key, const unsigned *__restrict__ val,
+						  unsigned long long *__restrict__ okey, unsigned *__restrict__ oval, int n, int tid,
+						  const unsigned *__restrict__ bloc, int nb)
 {
 	if (tid < n) {
+		const unsigned s0 = bloc[0];
+		int b = 0;
+		while (b + 1 < nb && bloc[b + 1] - s0 <= (unsigned)tid) b++;
+		const int lo = (int)(bloc[b] - s0), hi = (int)(bloc[b + 1] - s0);
 		const unsigned long long k0 = key[tid];
-		int r0 = 0;
-#pragma unroll 8
-		for (int j = 0; j < n; j++) r0 += key[j] < k0;
+		int r0 = lo;
+#pragma unroll 4
+		for (int j = lo; j < hi; j++) r0 += key[j] < k0;
 		okey[r0] = k0;
 		oval[r0] = val[tid];
 	}
@@ -132,8 +139,8 @@ __device__ __forceinline__ void rank_sort_one(const unsigned long long *__restri
 template <int RB> struct FwdCfg {
 	static constexpr int NPG = RB >= 2 ? RB / 2 : 1;     // 32-pixel groups (2 rows x 16 columns)
 	static constexpr int NEG = LGS_BATCH / 32;            // 32-entry groups per batch
-	static constexpr int NTASK = NPG * NEG;               // evaluate tasks per batch
-	static constexpr int NW = NTASK < 8 ? NTASK : 8;      // warps per CTA (>= NPG for every RB)
+	static constexpr int NTASK = NPG * NEG * 2;           // evaluate tasks per batch: (pixel group, entry group, row of the group)
+	static constexpr int NW = NTASK < 16 ? NTASK : 16;    // warps per CTA (>= NPG for every RB)
 	static constexpr int NT = NW * 32;
 	static constexpr int STAGE = 6 * 16 * LGS_BATCH + 4 * LGS_BATCH; // one staging buffer: 4 record quarters, feat, u, yp
 	// dynamic shared memory carve-up (bytes)
@@ -145,7 +152,7 @@ template <int RB> struct FwdCfg {
 	static constexpr size_t O_VALA = O_TILE + 4 * (size_t)NPG * 32 * LGS_TILE_LD;
 	static constexpr size_t O_VALB = O_VALA + 4 * LGS_SEG_CAP;
 	static constexpr size_t O_MASK = O_VALB + 4 * RANK_SORT_MAX;          // per (group, entry group): entries with alpha != 0
-	static constexpr size_t O_LIVE = O_MASK + 4 * NPG * NEG;              // per group: pixels not yet terminated
+	static constexpr size_t O_LIVE = O_MASK + 4 * NPG * NEG * 2;          // per group: pixels not yet terminated
 	static constexpr size_t O_LOC = O_LIVE + 4 * NPG;
 	static constexpr size_t BYTES = O_LOC + 4 * (LGS_NB + 1);
 };
@@ -185,7 +192,7 @@ __device__ __forceinline__ void stage_batch(const Stage &st, const float4 *__res
 }
 
 template <int RB>
-__global__ void __launch_bounds__(FwdCfg<RB>::NT)
+__global__ void __launch_bounds__(FwdCfg<RB>::NT, FwdCfg<RB>::NT >= 512 ? 2 : 1)
 render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ loc,
 		  const uint32_t *__restrict__ binbase, const uint32_t *__restrict__ order, uint4 *__restrict__ entries,
 		  const float *__restrict__ bg, const float *__restrict__ beams,
@@ -269,7 +276,7 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			const unsigned *sval = svalA;
 			if (!oversized && m > 1) {
 				if (m <= RANK_SORT_MAX) {
-					if (m <= NT) rank_sort_one<NT>(skeyA, svalA, skeyB, svalB, m, tid);
+					if (m <= NT) rank_sort_buckets<NT>(skeyA, svalA, skeyB, svalB, m, tid, sloc + k, k2 - k);
 					else rank_sort_small<NT>(skeyA, svalA, skeyB, svalB, m, tid);
 					skey = skeyB;
 					sval = svalB;
@@ -296,40 +303,45 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 					for (int i = 0; i < NPG; i++) any_live |= slive[i];
 					if (any_live == 0) { all_done = true; break; }
 				}
-				// evaluate: task = (pixel group, entry group); lane = entry, loop over the group's live pixels
+				// evaluate: task = (pixel group, entry group, row of the group); lane = entry, loop over the row's live pixels
 				for (int task = warp; task < C::NTASK; task += NW) {
-					const int pg = task % NPG, eg = task / NPG;
-					unsigned lv = slive[pg];
-					if (eg * 32 >= bn || lv == 0) {
-						if (lane == 0) smask[pg * NEG + eg] = 0;
-						continue;
-					}
+					const int pg = task % NPG, eg = (task / NPG) % NEG, h = task / (NPG * NEG);
+					unsigned lv = (slive[pg] >> (16 * h)) & 0xffffu;
 					const int j = eg * 32 + lane;
 					const bool valid = j < bn;
 					const int jj = valid ? j : 0;
+					const unsigned yp = st.yp[jj];
+					const int row = rg * RB + 2 * pg + h;
+					// the entry's rect covers this row (getRect_lidar's y range, aux.h:80-92)
+					const bool rowok = valid && row >= (int)(yp & 0xffffu) && row < (int)(yp >> 16);
+					if (eg * 32 >= bn || lv == 0 || !__any_sync(0xffffffffu, rowok)) {
+						if (lane == 0) smask[(pg * NEG + eg) * 2 + h] = 0;
+						if (eg * 32 < bn && lv != 0) { // pixels are live but no entry of this group covers the row
+							float *tz = tile + (size_t)(pg * 32 + 16 * h) * LD + j;
+							while (lv) {
+								const int p = __ffs(lv) - 1;
+								lv &= lv - 1;
+								tz[p * LD] = 0.f;
+							}
+						}
+						continue;
+					}
 					const float4 q0 = st.q[jj], q1 = st.q[B + jj], q2 = st.q[2 * B + jj], q3 = st.q[3 * B + jj];
 					const float4 uu = st.u[jj];
-					const unsigned yp = st.yp[jj];
-					const int ya = (int)(yp & 0xffffu), yb = (int)(yp >> 16);
-					const int row0 = rg * RB + 2 * pg;
-					// rows of this group the entry's rect covers (getRect_lidar's y range, aux.h:80-92):
-					// bit p>>4 of rsel says whether pixel p's row is inside
-					const unsigned rsel = ((valid && row0 >= ya && row0 < yb) ? 1u : 0u) |
-							      ((valid && row0 + 1 >= ya && row0 + 1 < yb) ? 2u : 0u);
-					float *tcol = tile + (size_t)(pg * 32) * LD + j;
-					const float4 *rays = sray + pg * 32;
+					float *tcol = tile + (size_t)(pg * 32 + 16 * h) * LD + j;
+					const float4 *rays = sray + pg * 32 + 16 * h;
 					float amax = 0.f;
 					while (lv) {
 						const int p = __ffs(lv) - 1;
 						lv &= lv - 1;
 						const float4 rr = rays[p];
 						float alpha = 0.f;
-						if ((rsel >> (p >> 4)) & 1u) alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, q0, q1, q2, q3, uu);
+						if (rowok) alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, q0, q1, q2, q3, uu);
 						tcol[p * LD] = alpha;
 						amax = fmaxf(amax, alpha);
 					}
 					const unsigned m32 = __ballot_sync(0xffffffffu, amax != 0.f);
-					if (lane == 0) smask[pg * NEG + eg] = m32;
+					if (lane == 0) smask[(pg * NEG + eg) * 2 + h] = m32;
 				}
 				__syncthreads();
 				if (blender) {
@@ -339,7 +351,7 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 						const float *trow = tile + (size_t)(warp * 32 + lane) * LD;
 #pragma unroll
 						for (int eg = 0; eg < NEG; eg++) {
-							const unsigned mw = smask[warp * NEG + eg];
+							const unsigned mw = smask[(warp * NEG + eg) * 2] | smask[(warp * NEG + eg) * 2 + 1];
 							for (int j0 = 0; j0 < 32; j0 += 4) {
 								const unsigned nib = (mw >> j0) & 0xfu;
 								if (nib == 0) continue;
