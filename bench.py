@@ -245,43 +245,97 @@ def main():
         h2d = sum(v.numel() * v.element_size() for v in h_in.values()) + sum(v.numel() * v.element_size() for v in h_anc.values())
         d2h = sum(v.numel() * v.element_size() for v in h_out.values())
 
-        def e2e_step():
-            g = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in h_in.items()}
-            am = h_anc["means"].to(dev, non_blocking=True)
-            as6 = h_anc["scales6"].to(dev, non_blocking=True)
-            ar = h_anc["rots"].to(dev, non_blocking=True)
-            h_out["anchor_radii"].copy_(rast.visible_filter(am, as6[:, :3], ar), non_blocking=True)
+        # Three-stream pipeline: while step k computes, the inputs of step k + 1 come up from pinned host memory and
+        # the results of step k - 1 (images + every gradient) go back; every step's copies are inside the timed region.
+        s_in, s_out, cur = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
+        NBUF = 2
+        h_all = dict(h_in, a_means=h_anc["means"], a_scales6=h_anc["scales6"], a_rots=h_anc["rots"])
+        d_bufs = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in h_all.items()} for _ in range(NBUF)]
+        h_outs = [h_out] + [{k: torch.empty_like(v).pin_memory() for k, v in h_out.items()} for _ in range(NBUF - 1)]
+        ev_in = [torch.cuda.Event() for _ in range(NBUF)]
+        ev_free = [torch.cuda.Event() for _ in range(NBUF)]
+        for e in ev_free:
+            e.record(cur)
+
+        dbg = [] if os.environ.get("LGS_E2E_DEBUG") else None
+
+        def upload(i):
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_free[i])  # the step that last read buffer set i has finished
+                if dbg is not None:
+                    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ea.record(s_in)
+                for k, v in h_all.items():
+                    d_bufs[i][k].copy_(v, non_blocking=True)
+                if dbg is not None:
+                    eb.record(s_in)
+                    dbg.append(("h2d", ea, eb))
+                ev_in[i].record(s_in)
+
+        def compute_download(i):
+            cur.wait_event(ev_in[i])
+            if dbg is not None:
+                ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ca.record(cur)
+            b = d_bufs[i]
+            g = {k: b[k].detach().requires_grad_(True) for k in h_in}
+            a_radii = rast.visible_filter(b["a_means"], b["a_scales6"][:, :3], b["a_rots"])
             m2d = torch.zeros((P, 4), device=dev, requires_grad=True)
             color, depth, occ, radii = rast(means3D=g["means3D"], means2D=m2d, shs=None, colors_precomp=g["colors"],
                                             opacities=g["opacities"], scales=g["scales"], rotations=g["rotations"],
                                             cov3D_precomp=None)
             torch.autograd.backward([color, depth, occ], [d["g_color"], d["g_depth"], d["g_occ"]])
-            h_out["color"].copy_(color.detach(), non_blocking=True)
-            h_out["depth"].copy_(depth.detach(), non_blocking=True)
-            h_out["occ"].copy_(occ.detach(), non_blocking=True)
             flat = torch.cat([g[k].grad.reshape(-1) for k in ("means3D", "scales", "rotations", "opacities", "colors")])
             if world > 1:
                 dist.all_reduce(flat)
-            h_out["bucket"].copy_(flat, non_blocking=True)
-            h_out["means2D"].copy_(m2d.grad, non_blocking=True)
+            ev_free[i].record(cur)
+            done = torch.cuda.Event()
+            done.record(cur)
+            if dbg is not None:
+                cb.record(cur)
+                dbg.append(("compute", ca, cb))
+                oa, ob = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            outs = dict(anchor_radii=a_radii, color=color.detach(), depth=depth.detach(), occ=occ.detach(), bucket=flat,
+                        means2D=m2d.grad)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                if dbg is not None:
+                    oa.record(s_out)
+                for k, t_ in outs.items():
+                    t_.record_stream(s_out)
+                    h_outs[i][k].copy_(t_, non_blocking=True)
+                if dbg is not None:
+                    ob.record(s_out)
+                    dbg.append(("d2h", oa, ob))
 
-        ke = max(3, min(args.steps, 50))
-        for _ in range(3):
-            e2e_step()
+        def run_pipeline(n):
+            upload(0)
+            for k in range(n):
+                if k + 1 < n:
+                    upload((k + 1) % NBUF)
+                compute_download(k % NBUF)
+            cur.wait_stream(s_out)
+
+        ke = max(4, min(args.steps, 50))
+        run_pipeline(4)
         barrier()
         e0.record()
-        for _ in range(ke):
-            e2e_step()
+        run_pipeline(ke)
         e1.record()
         barrier()
         ms_e = e0.elapsed_time(e1)
+        if dbg:
+            first = dbg[-3 * ke][1]
+            for name, a_, b_ in dbg[-30:]:
+                print(f"[e2e] {name:8s} start {first.elapsed_time(a_):8.3f} ms  dur {a_.elapsed_time(b_):6.3f} ms", file=sys.stderr)
         if world > 1:
             tt = torch.tensor([ms_e], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms_e = float(tt.item())
         e2e = {"value": world * 1e3 / (ms_e / ke), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": ke, "ms_per_step": ms_e / ke,
-               "api": "diff_lidargs_rasterization.GaussianRasterizer (autograd) + visible_filter"}
+               "api": "diff_lidargs_rasterization.GaussianRasterizer (autograd) + visible_filter; H2D / compute / D2H on three "
+                      "streams, double buffered"}
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -302,13 +356,13 @@ def main():
     cons = consumed_entries(fr, H, W, args.rows_per_bin)
     cons["touched"] = int((views["opacities"] != 0).sum().item()) if world == 1 else V
     alg = {  # bytes per launch
-        "clear": 80.0 * P,
+        "clear": 68.0 * P + 16.0 * cons["replayed"] + 80.0 * cons["touched"] + P / 8.0 + 8.0 * cons["nbins"] * 64,
         "project": 52.0 * P + 64.0 * V + 16.0 * P + 4.0 * P,
         "scan": 8.0 * cons["nbins"] * 64,
         "scatter": 16.0 * P + 16.0 * Ninst,
         "render_fwd": 32.0 * cons["sorted"] + 64.0 * cons["sorted"] + 24.0 * HW,
         "render_bwd": 16.0 * cons["replayed"] + 64.0 * cons["replayed"] + 24.0 * HW + 80.0 * cons["touched"],
-        "finalize_bwd": (80.0 + 44.0 + 68.0) * P,
+        "finalize_bwd": (80.0 + 44.0 + 68.0 + 4.0) * cons["touched"],
         "filter": 44.0 * A,
     }
     per = {}

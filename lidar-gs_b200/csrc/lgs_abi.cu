@@ -14,7 +14,8 @@
 namespace {
 
 thread_local char g_err[512] = "";
-thread_local FrameTotals *g_pinned = nullptr;
+thread_local FrameTotals *g_pinned = nullptr;     // mapped pinned host memory the scan kernel writes the frame totals into
+thread_local FrameTotals *g_pinned_dev = nullptr; // its device-side address
 thread_local long long g_last_instances = 0;
 std::atomic<int> g_rows_per_bin{0};
 std::atomic<int> g_sort_all{0};
@@ -121,7 +122,10 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn 
 	GeomPtrs gp = lgs_carve_geom(gb, g);
 	ImagePtrs ip = lgs_carve_image(ib, g);
 
-	if (!g_pinned) CK(cudaMallocHost((void **)&g_pinned, sizeof(FrameTotals)));
+	if (!g_pinned) {
+		CK(cudaHostAlloc((void **)&g_pinned, sizeof(FrameTotals), cudaHostAllocMapped));
+		CK(cudaHostGetDevicePointer((void **)&g_pinned_dev, g_pinned, 0));
+	}
 
 	g_timer.begin(LGS_STAGE_CLEAR, st);
 	CK(cudaMemsetAsync(gp.cnt, 0, (size_t)g.nbins * LGS_NB * 4, st));
@@ -132,11 +136,12 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn 
 			   viewmatrix, beam_inclinations, far, near, gp, radii, radii_xy, st);
 	g_timer.end(st);
 	g_timer.begin(LGS_STAGE_SCAN, st);
-	lgs_launch_scan(g, gp, st);
+	lgs_launch_scan(g, gp, g_pinned_dev, st);
 	g_timer.end(st);
 	g_launches += 3;
 	CK(cudaGetLastError());
-	CK(cudaMemcpyAsync(g_pinned, gp.totals, sizeof(FrameTotals), cudaMemcpyDeviceToHost, st));
+	// the scan kernel stored the totals straight into mapped host memory (a memcpy would queue behind whatever
+	// bulk device-to-host transfer the application has in flight on the copy engine)
 	CK(cudaStreamSynchronize(st));
 	const unsigned N = g_pinned->num_instances;
 	const unsigned long long R = g_pinned->num_rendered;
@@ -162,7 +167,11 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn 
 	return (int)R;
 }
 
-size_t lgs_backward_scratch_bytes(int P) { return lgs_al((size_t)(P > 0 ? P : 1) * LGS_GRAD_STRIDE * sizeof(float)); }
+// packed gradient rows [P, 20] followed by the "touched" bitmask (one bit per Gaussian)
+static size_t grad_rows_bytes(int P) { return lgs_al((size_t)(P > 0 ? P : 1) * LGS_GRAD_STRIDE * sizeof(float)); }
+static size_t touched_bytes(int P) { return lgs_al((((size_t)(P > 0 ? P : 1) + 31) / 32) * 4 + 16); } // bits + list length
+static size_t list_bytes(int P) { return lgs_al((size_t)(P > 0 ? P : 1) * 4); }
+size_t lgs_backward_scratch_bytes(int P) { return grad_rows_bytes(P) + touched_bytes(P) + list_bytes(P); }
 
 int lgs_backward(int P, int D, int M, int R, const float *background, int width, int height, const float *means3D,
 		 const float *shs, const float *colors_precomp, const float *scales, float scale_modifier,
@@ -190,7 +199,19 @@ int lgs_backward(int P, int D, int M, int R, const float *background, int width,
 	GeomPtrs gp = lgs_carve_geom(geom_buffer, g);
 	ImagePtrs ip = lgs_carve_image(image_buffer, g);
 	g_timer.begin(LGS_STAGE_CLEAR, st);
-	CK(cudaMemsetAsync(grad_scratch, 0, (size_t)P * LGS_GRAD_STRIDE * sizeof(float), st));
+	// only the rows of Gaussians that backward can touch are zeroed (by the mark kernel); the memset is the bitmask
+	uint32_t *touched = (uint32_t *)((char *)grad_scratch + grad_rows_bytes(P));
+	uint32_t *tlist = (uint32_t *)((char *)touched + touched_bytes(P)); // ids of touched Gaussians; length at touched[(P+31)/32]
+	CK(cudaMemsetAsync(touched, 0, touched_bytes(P), st));
+	lgs_launch_mark_touched(g, gp, ip, (const uint4 *)binning_buffer, grad_scratch, touched, tlist, st);
+	// every API gradient of an untouched Gaussian is zero: plain memsets, the finalize kernel only visits the list
+	CK(cudaMemsetAsync(dL_dmean2D, 0, (size_t)P * 16, st));
+	CK(cudaMemsetAsync(dL_dopacity, 0, (size_t)P * 4, st));
+	CK(cudaMemsetAsync(dL_dcolor, 0, (size_t)P * 8, st));
+	CK(cudaMemsetAsync(dL_dmean3D, 0, (size_t)P * 12, st));
+	if (dL_dcov3D) CK(cudaMemsetAsync(dL_dcov3D, 0, (size_t)P * 24, st));
+	if (dL_dscale) CK(cudaMemsetAsync(dL_dscale, 0, (size_t)P * 12, st));
+	if (dL_drot) CK(cudaMemsetAsync(dL_drot, 0, (size_t)P * 16, st));
 	g_timer.end(st);
 	g_timer.begin(LGS_STAGE_RENDER_BWD, st);
 	lgs_launch_render_bwd(g, gp, ip, (const uint4 *)binning_buffer, background, beam_inclinations, dL_dpix,
@@ -198,10 +219,10 @@ int lgs_backward(int P, int D, int M, int R, const float *background, int width,
 	g_timer.end(st);
 	g_timer.begin(LGS_STAGE_FINALIZE_BWD, st);
 	lgs_launch_finalize_bwd(g, means3D, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, radii,
-				grad_scratch, dL_dmean2D, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot,
+				grad_scratch, touched, tlist, dL_dmean2D, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot,
 				st);
 	g_timer.end(st);
-	g_launches += 2;
+	g_launches += 3;
 	CK(cudaGetLastError());
 	if (debug) CK(cudaStreamSynchronize(st));
 	return 0;

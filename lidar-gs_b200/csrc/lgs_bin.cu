@@ -43,7 +43,8 @@ scan_bins_kernel(int nbins, uint32_t *__restrict__ cnt, uint32_t *__restrict__ l
 
 // single block: exclusive scan of the per-bin totals (in place: binbase[b] holds total on entry)
 __global__ void __launch_bounds__(1024)
-scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__restrict__ totals, uint32_t *__restrict__ order)
+scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__restrict__ totals, uint32_t *__restrict__ order,
+		  FrameTotals *__restrict__ host_totals)
 {
 	__shared__ unsigned wsum[32];
 	__shared__ unsigned carry_s;
@@ -71,6 +72,12 @@ scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__rest
 	if (threadIdx.x == 0) {
 		binbase[nbins] = carry_s;
 		totals->num_instances = carry_s;
+		if (host_totals) { // mapped pinned host memory: the host reads the counts after a stream sync, no copy engine involved
+			FrameTotals t = *totals;
+			t.num_instances = carry_s;
+			*host_totals = t;
+			__threadfence_system();
+		}
 	}
 	// launch order of the render kernels: bins by descending size class (floor(log2(count)) + 1), so the
 	// longest lists start first and the tail of the grid is made of short ones
@@ -116,11 +123,11 @@ scatter_kernel(int P, int gx, int RB, const uint4 *__restrict__ aux, uint32_t *_
 
 } // namespace
 
-void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, cudaStream_t st)
+void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, cudaStream_t st)
 {
 	int warps_per_block = 8;
 	scan_bins_kernel<<<(g.nbins + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(g.nbins, gp.cnt, gp.loc, gp.binbase);
-	scan_total_kernel<<<1, 1024, 0, st>>>(g.nbins, gp.binbase, gp.totals, gp.order);
+	scan_total_kernel<<<1, 1024, 0, st>>>(g.nbins, gp.binbase, gp.totals, gp.order, host_totals);
 }
 
 void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, unsigned capacity, cudaStream_t st)

@@ -44,21 +44,20 @@ __global__ void __launch_bounds__(256)
 finalize_bwd_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ scales, float mod,
 		    const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
 		    const float *__restrict__ view, const int *__restrict__ radii, const float *__restrict__ grad,
-		    float *__restrict__ dL_dmean2D, float *__restrict__ dL_dopacity, float *__restrict__ dL_dcolor,
+		    const uint32_t *__restrict__ tlist, const uint32_t *__restrict__ tcount, float *__restrict__ dL_dmean2D, float *__restrict__ dL_dopacity, float *__restrict__ dL_dcolor,
 		    float *__restrict__ dL_dmean3D, float *__restrict__ dL_dcov3D, float *__restrict__ dL_dscale,
 		    float *__restrict__ dL_drot)
 {
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= P) return;
+	// grid-stride over the list of touched Gaussians (everything else was zero-filled by memsets)
+	const unsigned count = *tcount;
+	for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < count; it += gridDim.x * blockDim.x) {
+	const int idx = (int)tlist[it];
+	if (idx >= P || !(radii[idx] > 0)) continue;
 	float4 *m2 = reinterpret_cast<float4 *>(dL_dmean2D) + idx;
 	float2 *dc = reinterpret_cast<float2 *>(dL_dcolor) + idx;
 	float dm3[3] = {0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dsc[3] = {0.f, 0.f, 0.f},
 	      drt[4] = {0.f, 0.f, 0.f, 0.f};
-	if (!(radii[idx] > 0)) {
-		*m2 = make_float4(0.f, 0.f, 0.f, 0.f);
-		*dc = make_float2(0.f, 0.f);
-		dL_dopacity[idx] = 0.f;
-	} else {
+	{
 		const float4 *gq = reinterpret_cast<const float4 *>(grad + (size_t)idx * LGS_GRAD_STRIDE);
 		float gv[20];
 #pragma unroll
@@ -232,16 +231,62 @@ finalize_bwd_kernel(int P, const float *__restrict__ means3D, const float *__res
 	}
 	if (dL_dscale) { dL_dscale[3 * idx] = dsc[0]; dL_dscale[3 * idx + 1] = dsc[1]; dL_dscale[3 * idx + 2] = dsc[2]; }
 	if (dL_drot) reinterpret_cast<float4 *>(dL_drot)[idx] = make_float4(drt[0], drt[1], drt[2], drt[3]);
+	}
 }
 
 } // namespace
 
+namespace {
+
+// One CTA per bin: entries [0, deepest contributor of the bin) are what render_bwd replays.  The first CTA to
+// reach a Gaussian (atomicOr on its bit) zeroes its 80-byte accumulator row, so no P-sized memset is needed.
+__global__ void __launch_bounds__(512)
+mark_touched_kernel(FrameGeom g, const uint32_t *__restrict__ binbase, const uint32_t *__restrict__ n_contrib,
+		    const uint4 *__restrict__ entries, float *__restrict__ grad, uint32_t *__restrict__ touched,
+		    uint32_t *__restrict__ tlist, uint32_t *__restrict__ tcount)
+{
+	__shared__ unsigned smax;
+	const int bin = blockIdx.x, tid = threadIdx.x;
+	const int tx = bin % g.gx, rg = bin / g.gx;
+	if (tid == 0) smax = 0;
+	__syncthreads();
+	unsigned m = 0;
+	for (int i = tid; i < 16 * g.RB; i += 512) {
+		const int px = tx * LGS_TILE_X_ + (i & 15), py = rg * g.RB + (i >> 4);
+		if (px < g.W && py < g.H) m = max(m, n_contrib[(size_t)py * g.W + px]);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+	if ((tid & 31) == 0) atomicMax(&smax, m);
+	__syncthreads();
+	const unsigned maxc = smax, base = binbase[bin];
+	for (unsigned i = tid; i < maxc; i += 512) {
+		const unsigned id = entries[base + i].y, bit = 1u << (id & 31);
+		if (!(atomicOr(&touched[id >> 5], bit) & bit)) {
+			tlist[atomicAdd(tcount, 1u)] = id;
+			float4 *row = reinterpret_cast<float4 *>(grad + (size_t)id * LGS_GRAD_STRIDE);
+			const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+			row[0] = z; row[1] = z; row[2] = z; row[3] = z; row[4] = z;
+		}
+	}
+}
+
+} // namespace
+
+void lgs_launch_mark_touched(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, const uint4 *entries, float *grad,
+			     uint32_t *touched, uint32_t *tlist, cudaStream_t st)
+{
+	mark_touched_kernel<<<g.nbins, 512, 0, st>>>(g, gp.binbase, ip.n_contrib, entries, grad, touched, tlist,
+						     touched + ((size_t)g.P + 31) / 32);
+}
+
 void lgs_launch_finalize_bwd(const FrameGeom &g, const float *means3D, const float *scales, float mod,
 			     const float *rotations, const float *cov3D_precomp, const float *view, const int *radii,
-			     const float *grad, float *dL_dmean2D, float *dL_dopacity, float *dL_dcolor,
+			     const float *grad, const uint32_t *touched, const uint32_t *tlist, float *dL_dmean2D, float *dL_dopacity, float *dL_dcolor,
 			     float *dL_dmean3D, float *dL_dcov3D, float *dL_dscale, float *dL_drot, cudaStream_t st)
 {
-	finalize_bwd_kernel<<<(g.P + 255) / 256, 256, 0, st>>>(g.P, means3D, scales, mod, rotations, cov3D_precomp, view, radii,
-							       grad, dL_dmean2D, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D,
+	const int blocks = (int)min((long long)(g.P + 255) / 256, (long long)148 * 8);
+	finalize_bwd_kernel<<<blocks, 256, 0, st>>>(g.P, means3D, scales, mod, rotations, cov3D_precomp, view, radii, grad, tlist,
+						    touched + ((size_t)g.P + 31) / 32, dL_dmean2D, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D,
 							       dL_dscale, dL_drot);
 }

@@ -15,7 +15,7 @@ void lgs_launch_filter(int P, const float *means3D, const float *scales, float m
 void lgs_launch_mark_visible(int P, const float *means3D, const float *view, unsigned char *present, cudaStream_t st);
 
 // bucket counts -> per-bin exclusive offsets (loc), bin bases (binbase), totals->num_instances; cnt reset to 0
-void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, cudaStream_t st);
+void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, cudaStream_t st);
 // (Gaussian, bin) instances -> entries[], bin-major / bucket-minor, unordered inside a bucket
 void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, unsigned capacity, cudaStream_t st);
 
@@ -25,7 +25,10 @@ void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePt
 void lgs_launch_render_bwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, const uint4 *entries,
 			   const float *bg, const float *beams, const float *dL_dpix, const float *dL_ddepth,
 			   const float *dL_docc, float *grad, cudaStream_t st);
+// marks (bitmask) and zeroes the accumulator rows of every Gaussian in the part of the lists backward replays
+void lgs_launch_mark_touched(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, const uint4 *entries, float *grad,
+			     uint32_t *touched, uint32_t *tlist, cudaStream_t st);
 void lgs_launch_finalize_bwd(const FrameGeom &g, const float *means3D, const float *scales, float mod,
 			     const float *rotations, const float *cov3D_precomp, const float *view, const int *radii,
-			     const float *grad, float *dL_dmean2D, float *dL_dopacity, float *dL_dcolor,
+			     const float *grad, const uint32_t *touched, const uint32_t *tlist, float *dL_dmean2D, float *dL_dopacity, float *dL_dcolor,
 			     float *dL_dmean3D, float *dL_dcov3D, float *dL_dscale, float *dL_drot, cudaStream_t st);

@@ -8,7 +8,7 @@
 //     T_i (1 - accum_o,i) = T_final / (1 - alpha_i)                           running back-to-front blend)
 // so  dL/dalpha_i = T_i q_i - [rem_i - (g_occ - bg.g) T_final] / (1 - alpha_i),
 //     q_i = c_i.g_color + depth_i g_depth,   rem_i = (C_final - S_i).g_color + (D_final - SD_i) g_depth.
-// Per batch of LGS_BATCH entries, same CTA geometry and shared-memory tile as the forward kernel:
+// Per batch of BWD_BATCH entries, same CTA geometry and shared-memory tile as the forward kernel:
 //   1 evaluate : lanes = entries, loop over the group's live pixels -> alpha tile (exact forward arithmetic,
 //                so the contributing pairs are exactly the ones forward blended)
 //   2 scan     : lanes = pixels, serial over the touched entries: T, S -> tile A = dL/dalpha, tile B = alpha T
@@ -20,14 +20,17 @@
 
 namespace {
 
+#define BWD_BATCH 64                  // entries per batch of the backward replay
+#define BWD_LD (BWD_BATCH + 4)        // tile row stride, see LGS_TILE_LD
+
 template <int RB> struct BwdCfg {
 	static constexpr int NPG = RB >= 2 ? RB / 2 : 1;
-	static constexpr int NEG = LGS_BATCH / 32;
+	static constexpr int NEG = BWD_BATCH / 32;
 	static constexpr int NTASK = NPG * NEG * 2; // (pixel group, entry group, row of the group)
 	static constexpr int NW = NTASK < 16 ? NTASK : 16;
 	static constexpr int NT = NW * 32;
-	static constexpr size_t TILE = 4 * (size_t)NPG * 32 * LGS_TILE_LD;    // [group][pixel][LGS_TILE_LD]
-	static constexpr int STAGE = 6 * 16 * LGS_BATCH + 8 * LGS_BATCH;      // 4 record quarters, feat, u, yp, id
+	static constexpr size_t TILE = 4 * (size_t)NPG * 32 * BWD_LD;    // [group][pixel][BWD_LD]
+	static constexpr int STAGE = 6 * 16 * BWD_BATCH + 8 * BWD_BATCH;      // 4 record quarters, feat, u, yp, id
 	static constexpr size_t O_STAGE = 0;                                  // 2 staging buffers (double buffered)
 	static constexpr size_t O_RAY = O_STAGE + 2 * STAGE;                  // float4 ray per pixel
 	static constexpr size_t O_G = O_RAY + 16 * 32 * NPG;                  // float4 (g_color0, g_color1, g_depth, -) per pixel
@@ -49,10 +52,10 @@ struct BStage {
 	__device__ __forceinline__ BStage(unsigned char *base)
 	{
 		q = reinterpret_cast<float4 *>(base);
-		feat = q + 4 * LGS_BATCH;
-		u = feat + LGS_BATCH;
-		yp = reinterpret_cast<unsigned *>(u + LGS_BATCH);
-		id = yp + LGS_BATCH;
+		feat = q + 4 * BWD_BATCH;
+		u = feat + BWD_BATCH;
+		yp = reinterpret_cast<unsigned *>(u + BWD_BATCH);
+		id = yp + BWD_BATCH;
 	}
 };
 
@@ -63,7 +66,7 @@ __device__ __forceinline__ void bstage_batch(const BStage &st, const float4 *__r
 		const int j = i >> 2, part = i & 3;
 		const uint4 e = ent[j];
 		const float4 q = rec[4 * (size_t)e.y + part];
-		st.q[part * LGS_BATCH + j] = q;
+		st.q[part * BWD_BATCH + j] = q;
 		if (part == 0) { st.yp[j] = e.z; st.id[j] = e.y; }
 		else if (part == 1) st.feat[j].z = q.w;
 		else {
@@ -88,7 +91,7 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 		  const float *__restrict__ dL_docc, float *__restrict__ grad)
 {
 	using C = BwdCfg<RB>;
-	constexpr int NT = C::NT, NW = C::NW, NPG = C::NPG, NEG = C::NEG, B = LGS_BATCH, LD = LGS_TILE_LD;
+	constexpr int NT = C::NT, NW = C::NW, NPG = C::NPG, NEG = C::NEG, B = BWD_BATCH, LD = BWD_LD;
 	constexpr bool OVERLAP = NW > NPG;
 	extern __shared__ __align__(16) unsigned char smem[];
 	float4 *sray = reinterpret_cast<float4 *>(smem + C::O_RAY);

@@ -8,7 +8,8 @@
 // replays it) and composited in batches of LGS_BATCH entries.  As soon as every pixel of the bin has hit
 // the reference's T < 1e-4 stop the CTA quits: buckets behind the stop are never read, sorted or gathered.
 //
-// Compositing a batch is split into the part that is parallel and the part that is not:
+// Compositing a batch is split into the part that is parallel and the part that is not (and the two run on
+// different warps of the CTA, pipelined one batch apart):
 //   evaluate : alpha of every (entry, live pixel) pair.  LANES ARE ENTRIES, the loop runs over the live
 //              pixels of a 32-pixel group: the 64-B record stays in registers, the pixel's ray is a
 //              shared-memory broadcast, terminated pixels cost nothing (the reference -- and a
@@ -138,22 +139,23 @@ __device__ __forceinline__ void rank_sort_buckets(const unsigned long long *__re
 
 template <int RB> struct FwdCfg {
 	static constexpr int NPG = RB >= 2 ? RB / 2 : 1;     // 32-pixel groups (2 rows x 16 columns)
-	static constexpr int NEG = LGS_BATCH / 32;            // 32-entry groups per batch
-	static constexpr int NTASK = NPG * NEG * 2;           // evaluate tasks per batch: (pixel group, entry group, row of the group)
-	static constexpr int NW = NTASK < 16 ? NTASK : 16;    // warps per CTA (>= NPG for every RB)
+	static constexpr int NEV = 2 * NPG;                   // evaluate warps: one per (pixel group, row)
+	static constexpr int NW = NPG + NEV;                  // warps 0 .. NPG-1 blend, the rest evaluate
 	static constexpr int NT = NW * 32;
+	static constexpr int LPT = (4 * LGS_BATCH + NEV * 32 - 1) / (NEV * 32); // prefetch loads per evaluate thread
 	static constexpr int STAGE = 6 * 16 * LGS_BATCH + 4 * LGS_BATCH; // one staging buffer: 4 record quarters, feat, u, yp
+	static constexpr size_t TILE = 4 * (size_t)NPG * 32 * LGS_TILE_LD; // one alpha tile [group][pixel][LGS_TILE_LD]
 	// dynamic shared memory carve-up (bytes)
 	static constexpr size_t O_KEYA = 0;
 	static constexpr size_t O_KEYB = O_KEYA + 8 * LGS_SEG_CAP;
-	static constexpr size_t O_STAGE = O_KEYB + 8 * RANK_SORT_MAX;        // 2 staging buffers (double buffered)
-	static constexpr size_t O_RAY = O_STAGE + 2 * STAGE;                  // float4 per pixel of every group
-	static constexpr size_t O_TILE = O_RAY + 16 * 32 * NPG;               // alpha tile [group][pixel][LGS_TILE_LD]
-	static constexpr size_t O_VALA = O_TILE + 4 * (size_t)NPG * 32 * LGS_TILE_LD;
+	static constexpr size_t O_STAGE = O_KEYB + 8 * RANK_SORT_MAX;        // 3 staging buffers (ring)
+	static constexpr size_t O_RAY = O_STAGE + 3 * STAGE;                  // float4 per pixel of every group
+	static constexpr size_t O_TILE = O_RAY + 16 * 32 * NPG;               // 2 alpha tiles (double buffered)
+	static constexpr size_t O_VALA = O_TILE + 2 * TILE;
 	static constexpr size_t O_VALB = O_VALA + 4 * LGS_SEG_CAP;
-	static constexpr size_t O_MASK = O_VALB + 4 * RANK_SORT_MAX;          // per (group, entry group): entries with alpha != 0
-	static constexpr size_t O_LIVE = O_MASK + 4 * NPG * NEG * 2;          // per group: pixels not yet terminated
-	static constexpr size_t O_LOC = O_LIVE + 4 * NPG;
+	static constexpr size_t O_MASK = O_VALB + 4 * RANK_SORT_MAX;          // [2][group][row]: entries with alpha != 0
+	static constexpr size_t O_LIVE = O_MASK + 4 * 2 * NPG * 2;            // [2][group]: pixels not yet terminated
+	static constexpr size_t O_LOC = O_LIVE + 4 * 2 * NPG;
 	static constexpr size_t BYTES = O_LOC + 4 * (LGS_NB + 1);
 };
 
@@ -170,44 +172,43 @@ struct Stage {
 		u = feat + LGS_BATCH;
 		yp = reinterpret_cast<unsigned *>(u + LGS_BATCH);
 	}
-};
-
-// gather the records of entries [b0, b0 + bn) of the sorted chunk into a staging buffer: one float4 per thread
-__device__ __forceinline__ void stage_batch(const Stage &st, const float4 *__restrict__ rec, const unsigned long long *skey,
-					    const unsigned *sval, int b0, int bn, int t, int nthreads)
-{
-	for (int i = t; i < 4 * bn; i += nthreads) {
-		const int j = i >> 2, part = i & 3;
-		const unsigned id = (unsigned)skey[b0 + j];
-		const float4 q = rec[4 * (size_t)id + part];
-		st.q[part * LGS_BATCH + j] = q;
-		if (part == 0) st.yp[j] = sval[b0 + j];
-		else if (part == 1) st.feat[j].z = q.w;
+	// file quarter `part` of entry j's record (and what is derived from it)
+	__device__ __forceinline__ void put(int j, int part, const float4 &q_, unsigned yp_) const
+	{
+		q[part * LGS_BATCH + j] = q_;
+		if (part == 0) yp[j] = yp_;
+		else if (part == 1) feat[j].z = q_.w;
 		else {
-			const float uu = lgs_dot_self(q.x, q.y, q.z), r = lgs_div_prep(uu);
-			if (part == 2) { st.feat[j].x = q.w; st.u[j].x = uu; st.u[j].z = r; }
-			else { st.feat[j].y = q.w; st.u[j].y = uu; st.u[j].w = r; }
+			const float uu = lgs_dot_self(q_.x, q_.y, q_.z), r = lgs_div_prep(uu);
+			if (part == 2) { feat[j].x = q_.w; u[j].x = uu; u[j].z = r; }
+			else { feat[j].y = q_.w; u[j].y = uu; u[j].w = r; }
 		}
 	}
-}
+};
 
+// Warp-specialised software pipeline over the batches of a sorted chunk.  In iteration b the evaluate warps
+// compute the alpha tile of batch b (and prefetch the records of batch b + 1 into registers) while the blend
+// warps composite batch b - 1; one CTA barrier per iteration.  The evaluate warps therefore see the
+// "still live" pixel masks with a lag of one batch: a pixel that has just terminated is evaluated once more
+// for nothing, which never changes a result (the blend ignores terminated pixels).
 template <int RB>
-__global__ void __launch_bounds__(FwdCfg<RB>::NT, FwdCfg<RB>::NT >= 512 ? 2 : 1)
+__global__ void __launch_bounds__(FwdCfg<RB>::NT, FwdCfg<RB>::NT == 384 ? 2 : 1)
 render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ loc,
 		  const uint32_t *__restrict__ binbase, const uint32_t *__restrict__ order, uint4 *__restrict__ entries,
 		  const float *__restrict__ bg, const float *__restrict__ beams,
 		  float *__restrict__ final_T, uint32_t *__restrict__ n_contrib, uint32_t *__restrict__ sorted_end,
-		  float4 *__restrict__ fin, float *__restrict__ out_color, float *__restrict__ out_depth,
-		  float *__restrict__ out_occ, int sort_all)
+		  float4 *__restrict__ fin, uint4 *__restrict__ cta_prof, float *__restrict__ out_color,
+		  float *__restrict__ out_depth, float *__restrict__ out_occ, int sort_all)
 {
 	using C = FwdCfg<RB>;
-	constexpr int NT = C::NT, NW = C::NW, NPG = C::NPG, NEG = C::NEG, B = LGS_BATCH, LD = LGS_TILE_LD;
-	constexpr bool OVERLAP = NW > NPG; // spare warps prefetch the next batch while the blend warps composite
+	const long long clk0 = clock64();
+	const unsigned t0us = lgs_globaltimer_us();
+	constexpr int NT = C::NT, NPG = C::NPG, B = LGS_BATCH, LD = LGS_TILE_LD, NET = C::NEV * 32, LPT = C::LPT;
 	extern __shared__ __align__(16) unsigned char smem[];
 	unsigned long long *skeyA = reinterpret_cast<unsigned long long *>(smem + C::O_KEYA);
 	unsigned long long *skeyB = reinterpret_cast<unsigned long long *>(smem + C::O_KEYB);
 	float4 *sray = reinterpret_cast<float4 *>(smem + C::O_RAY);
-	float *tile = reinterpret_cast<float *>(smem + C::O_TILE);
+	float *tiles = reinterpret_cast<float *>(smem + C::O_TILE);
 	unsigned *svalA = reinterpret_cast<unsigned *>(smem + C::O_VALA);
 	unsigned *svalB = reinterpret_cast<unsigned *>(smem + C::O_VALB);
 	unsigned *smask = reinterpret_cast<unsigned *>(smem + C::O_MASK);
@@ -220,9 +221,9 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 	for (int i = tid; i < LGS_NB; i += NT) sloc[i] = loc[(size_t)bin * LGS_NB + i];
 	if (tid == 0) sloc[LGS_NB] = ntotal;
 
-	// blend state: warp w < NPG owns pixel group w, lane = pixel (row 2w + lane/16, column lane%16)
-	const int px = tx * LGS_TILE_X_ + (lane & 15), py = rg * RB + 2 * warp + (lane >> 4);
+	// blend warps: warp w < NPG owns pixel group w, lane = pixel (row 2w + lane/16, column lane%16)
 	const bool blender = warp < NPG;
+	const int px = tx * LGS_TILE_X_ + (lane & 15), py = rg * RB + 2 * warp + (lane >> 4);
 	const bool inside = blender && px < g.W && py < g.H && 2 * warp + (lane >> 4) < RB;
 	float T = 1.0f, C0 = 0.f, C1 = 0.f, D = 0.f;
 	unsigned last = 0, stop = 0; // stop: list position of the entry that terminated the pixel (diagnostic)
@@ -232,10 +233,13 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 		if (inside) ray = lgs_pixel_ray(px, py, g.W, g.H, beams);
 		sray[warp * 32 + lane] = make_float4(ray.x, ray.y, ray.z, 0.f);
 		const unsigned lv = __ballot_sync(0xffffffffu, inside);
-		if (lane == 0) slive[warp] = lv;
+		if (lane == 0) { slive[warp] = lv; slive[NPG + warp] = lv; }
 	}
+	// evaluate warps: (pixel group, row) fixed for the whole kernel
+	const int ew = warp - NPG, epg = blender ? 0 : ew % NPG, eh = blender ? 0 : ew / NPG, etid = tid - NPG * 32;
+	const int erow = rg * RB + 2 * epg + eh;
 	bool all_done = false;
-	int nstaged = 0; // batches staged so far: selects the staging buffer
+	unsigned gb = 0; // batches issued so far: parity selects tile / mask / live buffers, gb % 3 the staging buffer
 	__syncthreads();
 
 	int k = 0;
@@ -251,13 +255,6 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			if (n >= SEG_TARGET) break;
 		}
 		if (n == 0) { k = k2; continue; }
-		__syncthreads(); // slive is final for everything composited so far
-		if (!all_done) {
-			unsigned any_live = 0;
-#pragma unroll
-			for (int i = 0; i < NPG; i++) any_live |= slive[i];
-			all_done = any_live == 0;
-		}
 		if (all_done && !sort_all) break; // nothing behind this point is read, sorted or gathered
 		uint4 *seg = entries + base + s0;
 		const bool oversized = n > LGS_SEG_CAP;
@@ -290,116 +287,126 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 				}
 			}
 			if (all_done) continue; // sort_all mode: keep sorting, nothing left to blend
-			// ---- composite the m sorted entries in batches (staging is double buffered) ----
-			stage_batch(Stage(smem + C::O_STAGE + (nstaged & 1) * C::STAGE), rec, skey, sval, 0, min(B, m), tid, NT);
-			nstaged++;
-			for (int b0 = 0; b0 < m; b0 += B) {
-				const int bn = min(B, m - b0);
-				const Stage st(smem + C::O_STAGE + ((nstaged - 1) & 1) * C::STAGE);
-				__syncthreads(); // batch staged; previous batch blended (slive, tile free)
-				{
-					unsigned any_live = 0;
-#pragma unroll
-					for (int i = 0; i < NPG; i++) any_live |= slive[i];
-					if (any_live == 0) { all_done = true; break; }
+			// ---- composite the m sorted entries: pipeline over nb batches ----
+			const int nb = (m + B - 1) / B;
+			{ // prologue: stage batch 0 with every thread
+				const Stage st0(smem + C::O_STAGE + (gb % 3) * C::STAGE);
+				for (int i = tid; i < 4 * min(B, m); i += NT) {
+					const int j = i >> 2, part = i & 3;
+					st0.put(j, part, rec[4 * (size_t)(unsigned)skey[j] + part], sval[j]);
 				}
-				// evaluate: task = (pixel group, entry group, row of the group); lane = entry, loop over the row's live pixels
-				for (int task = warp; task < C::NTASK; task += NW) {
-					const int pg = task % NPG, eg = (task / NPG) % NEG, h = task / (NPG * NEG);
-					unsigned lv = (slive[pg] >> (16 * h)) & 0xffffu;
-					const int j = eg * 32 + lane;
-					const bool valid = j < bn;
-					const int jj = valid ? j : 0;
-					const unsigned yp = st.yp[jj];
-					const int row = rg * RB + 2 * pg + h;
-					// the entry's rect covers this row (getRect_lidar's y range, aux.h:80-92)
-					const bool rowok = valid && row >= (int)(yp & 0xffffu) && row < (int)(yp >> 16);
-					if (eg * 32 >= bn || lv == 0 || !__any_sync(0xffffffffu, rowok)) {
-						if (lane == 0) smask[(pg * NEG + eg) * 2 + h] = 0;
-						if (eg * 32 < bn && lv != 0) { // pixels are live but no entry of this group covers the row
-							float *tz = tile + (size_t)(pg * 32 + 16 * h) * LD + j;
+			}
+			__syncthreads();
+			for (int b = 0; b <= nb; b++) {
+				const unsigned gcur = gb + b; // global index of batch b
+				if (!blender) {
+					// ---------------- evaluate warps ----------------
+					float4 pre[LPT];
+					const int nnext = (b + 1 < nb) ? min(B, m - (b + 1) * B) : 0;
+#pragma unroll
+					for (int l = 0; l < LPT; l++) { // prefetch batch b + 1 into registers (latency hidden by the evaluate)
+						const int i = etid + l * NET;
+						if (i < 4 * nnext) pre[l] = rec[4 * (size_t)(unsigned)skey[(b + 1) * B + (i >> 2)] + (i & 3)];
+					}
+					if (b < nb) {
+						const int bn = min(B, m - b * B);
+						const Stage st(smem + C::O_STAGE + (gcur % 3) * C::STAGE);
+						float *tile = tiles + (gcur & 1) * (C::TILE / 4);
+						unsigned lv = (slive[(gcur & 1) * NPG + epg] >> (16 * eh)) & 0xffffu;
+						const bool valid = lane < bn;
+						const int jj = valid ? lane : 0;
+						const unsigned yp = st.yp[jj];
+						// the entry's rect covers this row (getRect_lidar's y range, aux.h:80-92)
+						const bool rowok = valid && erow >= (int)(yp & 0xffffu) && erow < (int)(yp >> 16);
+						float *tcol = tile + (size_t)(epg * 32 + 16 * eh) * LD + lane;
+						unsigned m32 = 0;
+						if (lv != 0 && __any_sync(0xffffffffu, rowok)) {
+							const float4 q0 = st.q[jj], q1 = st.q[B + jj], q2 = st.q[2 * B + jj], q3 = st.q[3 * B + jj];
+							const float4 uu = st.u[jj];
+							const float4 *rays = sray + epg * 32 + 16 * eh;
+							float amax = 0.f;
 							while (lv) {
 								const int p = __ffs(lv) - 1;
 								lv &= lv - 1;
-								tz[p * LD] = 0.f;
+								const float4 rr = rays[p];
+								float alpha = 0.f;
+								if (rowok) alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, q0, q1, q2, q3, uu);
+								tcol[p * LD] = alpha;
+								amax = fmaxf(amax, alpha);
+							}
+							m32 = __ballot_sync(0xffffffffu, amax != 0.f);
+						} else {
+							while (lv) { // live pixels, but no entry of the batch covers this row
+								const int p = __ffs(lv) - 1;
+								lv &= lv - 1;
+								tcol[p * LD] = 0.f;
 							}
 						}
-						continue;
+						if (lane == 0) smask[((gcur & 1) * NPG + epg) * 2 + eh] = m32;
 					}
-					const float4 q0 = st.q[jj], q1 = st.q[B + jj], q2 = st.q[2 * B + jj], q3 = st.q[3 * B + jj];
-					const float4 uu = st.u[jj];
-					float *tcol = tile + (size_t)(pg * 32 + 16 * h) * LD + j;
-					const float4 *rays = sray + pg * 32 + 16 * h;
-					float amax = 0.f;
-					while (lv) {
-						const int p = __ffs(lv) - 1;
-						lv &= lv - 1;
-						const float4 rr = rays[p];
-						float alpha = 0.f;
-						if (rowok) alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, q0, q1, q2, q3, uu);
-						tcol[p * LD] = alpha;
-						amax = fmaxf(amax, alpha);
-					}
-					const unsigned m32 = __ballot_sync(0xffffffffu, amax != 0.f);
-					if (lane == 0) smask[(pg * NEG + eg) * 2 + h] = m32;
-				}
-				__syncthreads();
-				if (blender) {
-					// blend: lane = pixel, serial over the entries that touch this group, four at a time
-					if (!__all_sync(0xffffffffu, done)) {
-						const unsigned pos0 = s0 + c0 + b0;
-						const float *trow = tile + (size_t)(warp * 32 + lane) * LD;
+					if (nnext) {
+						const Stage stn(smem + C::O_STAGE + ((gcur + 1) % 3) * C::STAGE);
 #pragma unroll
-						for (int eg = 0; eg < NEG; eg++) {
-							const unsigned mw = smask[(warp * NEG + eg) * 2] | smask[(warp * NEG + eg) * 2 + 1];
-							for (int j0 = 0; j0 < 32; j0 += 4) {
-								const unsigned nib = (mw >> j0) & 0xfu;
-								if (nib == 0) continue;
-								const int jb = eg * 32 + j0;
-								const float4 a4 = *reinterpret_cast<const float4 *>(trow + jb);
-								const float4 f0 = st.feat[jb], f1 = st.feat[jb + 1], f2 = st.feat[jb + 2], f3 = st.feat[jb + 3];
+						for (int l = 0; l < LPT; l++) {
+							const int i = etid + l * NET;
+							if (i < 4 * nnext) stn.put(i >> 2, i & 3, pre[l], sval[(b + 1) * B + (i >> 2)]);
+						}
+					}
+				} else if (b >= 1) {
+					// ---------------- blend warps: batch b - 1 ----------------
+					const unsigned gprev = gcur - 1;
+					if (!__all_sync(0xffffffffu, done)) {
+						const Stage st(smem + C::O_STAGE + (gprev % 3) * C::STAGE);
+						const float *trow = tiles + (gprev & 1) * (C::TILE / 4) + (size_t)(warp * 32 + lane) * LD;
+						const unsigned pos0 = s0 + c0 + (unsigned)(b - 1) * B;
+						const unsigned mw = smask[((gprev & 1) * NPG + warp) * 2] | smask[((gprev & 1) * NPG + warp) * 2 + 1];
+						for (int j0 = 0; j0 < B; j0 += 4) {
+							const unsigned nib = (mw >> j0) & 0xfu;
+							if (nib == 0) continue;
+							const float4 a4 = *reinterpret_cast<const float4 *>(trow + j0);
+							const float4 f0 = st.feat[j0], f1 = st.feat[j0 + 1], f2 = st.feat[j0 + 2], f3 = st.feat[j0 + 3];
 #define LGS_BLEND1(al_, f_, bit_)                                                                  \
 	if ((nib & (1u << bit_)) && al_ != 0.f && !done) {                                         \
 		const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al_));                           \
 		if (test_T < 0.0001f) {                                                            \
 			done = true;                                                               \
-			stop = pos0 + jb + bit_ + 1;                                               \
+			stop = pos0 + j0 + bit_ + 1;                                               \
 		} else {                                                                           \
 			C0 = __fmaf_rn(T, __fmul_rn(al_, f_.x), C0);                               \
 			C1 = __fmaf_rn(T, __fmul_rn(al_, f_.y), C1);                               \
 			D = __fmaf_rn(T, __fmul_rn(al_, f_.z), D);                                 \
 			T = test_T;                                                                \
-			last = pos0 + jb + bit_ + 1;                                               \
+			last = pos0 + j0 + bit_ + 1;                                               \
 		}                                                                                  \
 	}
-								LGS_BLEND1(a4.x, f0, 0)
-								LGS_BLEND1(a4.y, f1, 1)
-								LGS_BLEND1(a4.z, f2, 2)
-								LGS_BLEND1(a4.w, f3, 3)
+							LGS_BLEND1(a4.x, f0, 0)
+							LGS_BLEND1(a4.y, f1, 1)
+							LGS_BLEND1(a4.z, f2, 2)
+							LGS_BLEND1(a4.w, f3, 3)
 #undef LGS_BLEND1
-							}
 						}
-						const unsigned lv = __ballot_sync(0xffffffffu, !done);
-						if (lane == 0) slive[warp] = lv;
 					}
-					if (!OVERLAP && b0 + B < m) { // no spare warps: every warp stages after its blend
-						__syncthreads();
-						stage_batch(Stage(smem + C::O_STAGE + (nstaged & 1) * C::STAGE), rec, skey, sval, b0 + B,
-							    min(B, m - b0 - B), tid, NT);
-					}
-				} else if (b0 + B < m) {
-					// spare warps: prefetch the next batch into the other staging buffer meanwhile
-					stage_batch(Stage(smem + C::O_STAGE + (nstaged & 1) * C::STAGE), rec, skey, sval, b0 + B,
-						    min(B, m - b0 - B), tid - NPG * 32, NT - NPG * 32);
+					const unsigned lvn = __ballot_sync(0xffffffffu, !done);
+					if (lane == 0) slive[(gprev & 1) * NPG + warp] = lvn;
 				}
-				if (b0 + B < m) nstaged++;
+				__syncthreads();
+				if (b >= 1) { // the masks the blend of batch b - 1 just published
+					unsigned any_live = 0;
+#pragma unroll
+					for (int i = 0; i < NPG; i++) any_live |= slive[((gcur - 1) & 1) * NPG + i];
+					if (any_live == 0) { all_done = true; break; }
+				}
 			}
+			gb += nb;
 			if (all_done && !sort_all) break;
 		}
 		k = k2;
 		if (all_done && !sort_all) break;
 	}
-	if (tid == 0) sorted_end[bin] = (k < LGS_NB) ? sloc[k] : ntotal;
+	if (tid == 0) {
+		sorted_end[bin] = (k < LGS_NB) ? sloc[k] : ntotal;
+		cta_prof[bin] = make_uint4(t0us, (unsigned)(clock64() - clk0), lgs_smid(), gb);
+	}
 	if (inside) {
 		const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
 		final_T[pix] = T;
@@ -423,7 +430,7 @@ void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uin
 		configured = true;
 	}
 	render_fwd_kernel<RB><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, gp.order, entries, bg, beams,
-								 ip.final_T, ip.n_contrib, ip.sorted_end, ip.fin, out_color,
+								 ip.final_T, ip.n_contrib, ip.sorted_end, ip.fin, ip.cta_prof, out_color,
 								 out_depth, out_occ, sort_all);
 }
 
