@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--rows-per-bin", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--pose-rank", type=int, default=None, help="debug: render the frame rank K would render")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,7 +169,7 @@ def main():
     L.lgs_set_rows_per_bin(args.rows_per_bin)
 
     sc = synth.make_config(CFG)
-    sc["viewmatrix"] = rank_pose(sc, rank)
+    sc["viewmatrix"] = rank_pose(sc, rank if args.pose_rank is None else args.pose_rank)
     anc = make_anchors(sc)
     P, H, W = sc["P"], sc["H"], sc["W"]
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)

@@ -79,22 +79,33 @@ scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__rest
 			__threadfence_system();
 		}
 	}
-	// launch order of the render kernels: bins by descending size class (floor(log2(count)) + 1), so the
-	// longest lists start first and the tail of the grid is made of short ones
+	// Launch order of the render kernels: bins by ASCENDING list length (64 linear classes).  A dense bin saturates
+	// after a few hundred entries whatever its length; the expensive bins are the sparse ones, whose rays never
+	// terminate and walk their whole list -- so short lists go first and the tail of the grid is made of the uniform,
+	// cheap, dense bins.
+	__shared__ unsigned smaxt;
+	if (threadIdx.x == 0) smaxt = 0;
 	__syncthreads();
+	unsigned mx = 0;
+	for (int i = threadIdx.x; i < nbins; i += 1024) mx = max(mx, binbase[i + 1] - binbase[i]);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	if (lane == 0) atomicMax(&smaxt, mx);
+	__syncthreads();
+	const unsigned long long maxt = (unsigned long long)smaxt + 1ull;
 	for (int i = threadIdx.x; i < nbins; i += 1024) {
 		unsigned t = binbase[i + 1] - binbase[i];
-		atomicAdd(&hist[t ? 32 - __clz(t) : 0], 1u);
+		atomicAdd(&hist[(unsigned)((unsigned long long)t * 32ull / maxt)], 1u);
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		unsigned run = 0;
-		for (int c = 32; c >= 0; c--) { start[c] = run; run += hist[c]; }
+		for (int c = 0; c < 33; c++) { start[c] = run; run += hist[c]; }
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < nbins; i += 1024) {
 		unsigned t = binbase[i + 1] - binbase[i];
-		order[atomicAdd(&start[t ? 32 - __clz(t) : 0], 1u)] = (unsigned)i;
+		order[atomicAdd(&start[(unsigned)((unsigned long long)t * 32ull / maxt)], 1u)] = (unsigned)i;
 	}
 }
 

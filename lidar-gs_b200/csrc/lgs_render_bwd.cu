@@ -23,8 +23,10 @@ namespace {
 #define BWD_BATCH 64                  // entries per batch of the backward replay
 #define BWD_LD (BWD_BATCH + 4)        // tile row stride, see LGS_TILE_LD
 
-template <int RB> struct BwdCfg {
-	static constexpr int NPG = RB >= 2 ? RB / 2 : 1;
+// One CTA per (bin, 32-pixel group): the lists are read-only here, so the groups of a bin need not share a CTA, and
+// a bin whose rays never terminate (thousands of replayed entries) is spread over RB/2 CTAs instead of serialising.
+struct BwdCfg {
+	static constexpr int NPG = 1;
 	static constexpr int NEG = BWD_BATCH / 32;
 	static constexpr int NTASK = NPG * NEG * 2; // (pixel group, entry group, row of the group)
 	static constexpr int NW = NTASK < 16 ? NTASK : 16;
@@ -82,15 +84,14 @@ __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float 
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int RB>
-__global__ void __launch_bounds__(BwdCfg<RB>::NT, BwdCfg<RB>::NT >= 512 ? 2 : 1)
+__global__ void __launch_bounds__(BwdCfg::NT)
 render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ binbase,
 		  const uint32_t *__restrict__ order, const uint4 *__restrict__ entries, const float *__restrict__ bg,
 		  const float *__restrict__ beams, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
 		  const float4 *__restrict__ fin, const float *__restrict__ dL_dpix, const float *__restrict__ dL_ddepth,
 		  const float *__restrict__ dL_docc, float *__restrict__ grad)
 {
-	using C = BwdCfg<RB>;
+	using C = BwdCfg;
 	constexpr int NT = C::NT, NW = C::NW, NPG = C::NPG, NEG = C::NEG, B = BWD_BATCH, LD = BWD_LD;
 	constexpr bool OVERLAP = NW > NPG;
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -103,16 +104,18 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 	unsigned *slive = reinterpret_cast<unsigned *>(smem + C::O_LIVE);
 	unsigned *smax = reinterpret_cast<unsigned *>(smem + C::O_MAX);
 
-	const int bin = (int)order[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int RB = g.RB, npgl = RB >= 2 ? RB / 2 : 1; // pixel groups per list bin
+	const int bin = (int)order[blockIdx.x / npgl], pgc = blockIdx.x % npgl; // this CTA's group inside the bin
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tx = bin % g.gx, rg = bin / g.gx;
 	const unsigned base = binbase[bin];
 	if (tid == 0) smax[0] = 0;
 	__syncthreads();
 
 	// scan state: warp w < NPG owns pixel group w, lane = pixel
-	const int px = tx * LGS_TILE_X_ + (lane & 15), py = rg * RB + 2 * warp + (lane >> 4);
+	const int px = tx * LGS_TILE_X_ + (lane & 15), py = rg * RB + 2 * pgc + (lane >> 4);
 	const bool blender = warp < NPG;
-	const bool inside = blender && px < g.W && py < g.H && 2 * warp + (lane >> 4) < RB;
+	const bool inside = blender && px < g.W && py < g.H && 2 * pgc + (lane >> 4) < RB;
 	float T = 1.f, S0 = 0.f, S1 = 0.f, SD = 0.f;
 	float C0f = 0.f, C1f = 0.f, Df = 0.f, g0 = 0.f, g1 = 0.f, gd = 0.f, kocc = 0.f;
 	unsigned lastc = 0;
@@ -164,7 +167,7 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			const bool valid = j < bn;
 			const int jj = valid ? j : 0;
 			const unsigned yp = st.yp[jj];
-			const int row = rg * RB + 2 * pg + h;
+			const int row = rg * RB + 2 * pgc + h;
 			const bool rowok = valid && row >= (int)(yp & 0xffffu) && row < (int)(yp >> 16);
 			if (eg * 32 >= bn || lv == 0 || !__any_sync(0xffffffffu, rowok)) {
 				if (lane == 0) smask[(pg * NEG + eg) * 2 + h] = 0;
@@ -302,32 +305,19 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 	}
 }
 
-template <int RB>
-void launch_bwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, const uint4 *entries, const float *bg,
-		const float *beams, const float *dL_dpix, const float *dL_ddepth, const float *dL_docc, float *grad,
-		cudaStream_t st)
-{
-	using C = BwdCfg<RB>;
-	static bool configured = false;
-	if (!configured) {
-		cudaFuncSetAttribute(render_bwd_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
-		configured = true;
-	}
-	render_bwd_kernel<RB><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.binbase, gp.order, entries, bg, beams, ip.final_T,
-								 ip.n_contrib, ip.fin, dL_dpix, dL_ddepth, dL_docc, grad);
-}
-
 } // namespace
 
 void lgs_launch_render_bwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, const uint4 *entries,
 			   const float *bg, const float *beams, const float *dL_dpix, const float *dL_ddepth,
 			   const float *dL_docc, float *grad, cudaStream_t st)
 {
-	switch (g.RB) {
-	case 1: launch_bwd<1>(g, gp, ip, entries, bg, beams, dL_dpix, dL_ddepth, dL_docc, grad, st); break;
-	case 2: launch_bwd<2>(g, gp, ip, entries, bg, beams, dL_dpix, dL_ddepth, dL_docc, grad, st); break;
-	case 4: launch_bwd<4>(g, gp, ip, entries, bg, beams, dL_dpix, dL_ddepth, dL_docc, grad, st); break;
-	case 8: launch_bwd<8>(g, gp, ip, entries, bg, beams, dL_dpix, dL_ddepth, dL_docc, grad, st); break;
-	default: launch_bwd<16>(g, gp, ip, entries, bg, beams, dL_dpix, dL_ddepth, dL_docc, grad, st); break;
+	using C = BwdCfg;
+	static bool configured = false;
+	if (!configured) {
+		cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+		configured = true;
 	}
+	const int npgl = g.RB >= 2 ? g.RB / 2 : 1;
+	render_bwd_kernel<<<g.nbins * npgl, C::NT, C::BYTES, st>>>(g, gp.rec, gp.binbase, gp.order, entries, bg, beams, ip.final_T,
+								   ip.n_contrib, ip.fin, dL_dpix, dL_ddepth, dL_docc, grad);
 }

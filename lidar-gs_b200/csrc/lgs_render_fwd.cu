@@ -156,7 +156,12 @@ template <int RB> struct FwdCfg {
 	static constexpr size_t O_MASK = O_VALB + 4 * RANK_SORT_MAX;          // [2][group][row]: entries with alpha != 0
 	static constexpr size_t O_LIVE = O_MASK + 4 * 2 * NPG * 2;            // [2][group]: pixels not yet terminated
 	static constexpr size_t O_LOC = O_LIVE + 4 * 2 * NPG;
-	static constexpr size_t BYTES = O_LOC + 4 * (LGS_NB + 1);
+	static constexpr size_t O_TAIL = (O_LOC + 4 * (LGS_NB + 1) + 15) / 16 * 16; // straggler state: TL x (float4 + uint4)
+	static constexpr int TL = 2 * NW;                     // switch to straggler mode when <= TL pixels of the bin are live
+	static constexpr size_t BYTES = O_TAIL + 32 * TL;
+	// straggler mode stages whole sub-chunks of TSUB entries (100 B each) in the memory of the two alpha tiles
+	static constexpr int TSUB_ = (int)(2 * TILE / 100) / 32 * 32;
+	static constexpr int TSUB = TSUB_ < 256 ? TSUB_ : 256;
 };
 
 // views into one staging buffer
@@ -238,6 +243,11 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 	// evaluate warps: (pixel group, row) fixed for the whole kernel
 	const int ew = warp - NPG, epg = blender ? 0 : ew % NPG, eh = blender ? 0 : ew / NPG, etid = tid - NPG * 32;
 	const int erow = rg * RB + 2 * epg + eh;
+	// straggler mode (see below): per-slot pixel state lives in shared memory between segments
+	float4 *ts0 = reinterpret_cast<float4 *>(smem + C::O_TAIL);        // T, C0, C1, D
+	uint4 *ts1 = reinterpret_cast<uint4 *>(smem + C::O_TAIL) + C::TL;  // last, stop, pixel (group * 32 + lane), done
+	bool tail = false;
+	int ntail = 0, myslot = -1;
 	bool all_done = false;
 	unsigned gb = 0; // batches issued so far: parity selects tile / mask / live buffers, gb % 3 the staging buffer
 	__syncthreads();
@@ -287,6 +297,100 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 				}
 			}
 			if (all_done) continue; // sort_all mode: keep sorting, nothing left to blend
+			if (!tail) {
+				// Straggler mode.  Once only a handful of pixels of the bin are still live (rays that found no
+				// dense surface yet), the batch pipeline is all latency: a barrier, a record prefetch and a
+				// 32-wide evaluate per 32 entries, for one or two pixels.  From here on every live pixel gets a
+				// WARP: lanes = entries, a whole sorted sub-chunk is staged at once, alpha is evaluated 32 entries
+				// at a time and blended inside the warp (ballot + shuffle), with no CTA barrier per batch.
+				int nlive = 0;
+#pragma unroll
+				for (int i = 0; i < NPG; i++) nlive += __popc(slive[((gb + 1) & 1) * NPG + i]);
+				if (nlive <= C::TL) {
+					tail = true;
+					ntail = nlive;
+					if (blender) {
+						int slot0 = 0;
+						for (int i = 0; i < warp; i++) slot0 += __popc(slive[((gb + 1) & 1) * NPG + i]);
+						const unsigned lvm = __ballot_sync(0xffffffffu, !done);
+						if (!done) {
+							myslot = slot0 + __popc(lvm & ((1u << lane) - 1u));
+							ts0[myslot] = make_float4(T, C0, C1, D);
+							ts1[myslot] = make_uint4(last, stop, (unsigned)(warp * 32 + lane), 0u);
+						}
+					}
+					__syncthreads();
+				}
+			}
+			if (tail) {
+				float4 *tq = reinterpret_cast<float4 *>(smem + C::O_TILE);  // tq[part * TSUB + j]
+				float4 *tfeat = tq + 4 * C::TSUB, *tu = tfeat + C::TSUB;
+				unsigned *typ = reinterpret_cast<unsigned *>(tu + C::TSUB);
+				for (int sub0 = 0; sub0 < m; sub0 += C::TSUB) {
+					const int sm = min(C::TSUB, m - sub0);
+					__syncthreads(); // staging area free
+					for (int i = tid; i < 4 * sm; i += NT) {
+						const int j = i >> 2, part = i & 3;
+						const float4 q = rec[4 * (size_t)(unsigned)skey[sub0 + j] + part];
+						tq[part * C::TSUB + j] = q;
+						if (part == 0) typ[j] = sval[sub0 + j];
+						else if (part == 1) tfeat[j].z = q.w;
+						else {
+							const float uu = lgs_dot_self(q.x, q.y, q.z), r = lgs_div_prep(uu);
+							if (part == 2) { tfeat[j].x = q.w; tu[j].x = uu; tu[j].z = r; }
+							else { tfeat[j].y = q.w; tu[j].y = uu; tu[j].w = r; }
+						}
+					}
+					__syncthreads();
+					for (int slot = warp; slot < ntail; slot += C::NW) {
+						uint4 s1 = ts1[slot];
+						if (s1.w) continue; // this pixel has terminated
+						float4 s0v = ts0[slot];
+						const float4 rr = sray[s1.z];
+						const int prow = rg * RB + 2 * (int)(s1.z >> 5) + (int)((s1.z >> 4) & 1u);
+						const unsigned posb = s0 + c0 + (unsigned)sub0;
+						bool fin_ = false;
+						for (int g0 = 0; g0 < sm && !fin_; g0 += 32) {
+							const int j = g0 + lane;
+							const bool valid = j < sm;
+							const int jj = valid ? j : 0;
+							const unsigned yp = typ[jj];
+							float alpha = 0.f;
+							if (valid && prow >= (int)(yp & 0xffffu) && prow < (int)(yp >> 16))
+								alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, tq[jj], tq[C::TSUB + jj], tq[2 * C::TSUB + jj],
+										       tq[3 * C::TSUB + jj], tu[jj]);
+							unsigned msk = __ballot_sync(0xffffffffu, alpha != 0.f);
+							while (msk) {
+								const int b = __ffs(msk) - 1;
+								msk &= msk - 1;
+								const float al = __shfl_sync(0xffffffffu, alpha, b);
+								const float4 f = tfeat[g0 + b];
+								const float test_T = __fmul_rn(s0v.x, __fsub_rn(1.0f, al));
+								if (test_T < 0.0001f) {
+									fin_ = true;
+									s1.y = posb + g0 + b + 1;
+									s1.w = 1u;
+									break;
+								}
+								s0v.y = __fmaf_rn(s0v.x, __fmul_rn(al, f.x), s0v.y);
+								s0v.z = __fmaf_rn(s0v.x, __fmul_rn(al, f.y), s0v.z);
+								s0v.w = __fmaf_rn(s0v.x, __fmul_rn(al, f.z), s0v.w);
+								s0v.x = test_T;
+								s1.x = posb + g0 + b + 1;
+							}
+						}
+						if (lane == 0) { ts0[slot] = s0v; ts1[slot] = s1; }
+					}
+				}
+				__syncthreads();
+				{
+					unsigned alive = 0;
+					for (int i = 0; i < ntail; i++) alive |= ts1[i].w ^ 1u;
+					all_done = alive == 0;
+				}
+				if (all_done && !sort_all) break;
+				continue;
+			}
 			// ---- composite the m sorted entries: pipeline over nb batches ----
 			const int nb = (m + B - 1) / B;
 			{ // prologue: stage batch 0 with every thread
@@ -403,9 +507,15 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 		k = k2;
 		if (all_done && !sort_all) break;
 	}
+	if (myslot >= 0) { // pixels that finished in straggler mode: their state lives in shared memory
+		const float4 a = ts0[myslot];
+		const uint4 b = ts1[myslot];
+		T = a.x; C0 = a.y; C1 = a.z; D = a.w;
+		last = b.x; stop = b.y;
+	}
 	if (tid == 0) {
 		sorted_end[bin] = (k < LGS_NB) ? sloc[k] : ntotal;
-		cta_prof[bin] = make_uint4(t0us, (unsigned)(clock64() - clk0), lgs_smid(), gb);
+		cta_prof[bin] = make_uint4(t0us, (unsigned)(clock64() - clk0), lgs_smid(), gb | (tail ? 0x80000000u : 0u) | ((unsigned)ntail << 24));
 	}
 	if (inside) {
 		const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
