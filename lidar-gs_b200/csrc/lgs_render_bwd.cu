@@ -32,7 +32,7 @@ struct BwdCfg {
 	static constexpr int NW = NTASK < 16 ? NTASK : 16;
 	static constexpr int NT = NW * 32;
 	static constexpr size_t TILE = 4 * (size_t)NPG * 32 * BWD_LD;    // [group][pixel][BWD_LD]
-	static constexpr int STAGE = 6 * 16 * BWD_BATCH + 8 * BWD_BATCH;      // 4 record quarters, feat, u, yp, id
+	static constexpr int STAGE = 6 * 16 * BWD_BATCH + 12 * BWD_BATCH;     // 4 record quarters, feat, u, yp, id, row flags
 	static constexpr size_t O_STAGE = 0;                                  // 2 staging buffers (double buffered)
 	static constexpr size_t O_RAY = O_STAGE + 2 * STAGE;                  // float4 ray per pixel
 	static constexpr size_t O_G = O_RAY + 16 * 32 * NPG;                  // float4 (g_color0, g_color1, g_depth, -) per pixel
@@ -51,6 +51,7 @@ struct BStage {
 	float4 *u;     // (|u1|^2, |u2|^2, refined 1/|u1|^2, refined 1/|u2|^2)
 	unsigned *yp;  // y0 | y1 << 16
 	unsigned *id;  // Gaussian index
+	unsigned *flag; // bit (2 * group + row): forward blended this entry into a pixel of that row
 	__device__ __forceinline__ BStage(unsigned char *base)
 	{
 		q = reinterpret_cast<float4 *>(base);
@@ -58,6 +59,7 @@ struct BStage {
 		u = feat + BWD_BATCH;
 		yp = reinterpret_cast<unsigned *>(u + BWD_BATCH);
 		id = yp + BWD_BATCH;
+		flag = id + BWD_BATCH;
 	}
 };
 
@@ -69,7 +71,7 @@ __device__ __forceinline__ void bstage_batch(const BStage &st, const float4 *__r
 		const uint4 e = ent[j];
 		const float4 q = rec[4 * (size_t)e.y + part];
 		st.q[part * BWD_BATCH + j] = q;
-		if (part == 0) { st.yp[j] = e.z; st.id[j] = e.y; }
+		if (part == 0) { st.yp[j] = e.z; st.id[j] = e.y; st.flag[j] = e.w; }
 		else if (part == 1) st.feat[j].z = q.w;
 		else {
 			const float uu = lgs_dot_self(q.x, q.y, q.z), r = lgs_div_prep(uu);
@@ -168,7 +170,8 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			const int jj = valid ? j : 0;
 			const unsigned yp = st.yp[jj];
 			const int row = rg * RB + 2 * pgc + h;
-			const bool rowok = valid && row >= (int)(yp & 0xffffu) && row < (int)(yp >> 16);
+			// only (entry, row) pairs forward blended something in can contribute: everything else is skipped unevaluated
+			const bool rowok = valid && ((st.flag[jj] >> (2 * pgc + h)) & 1u) && row >= (int)(yp & 0xffffu) && row < (int)(yp >> 16);
 			if (eg * 32 >= bn || lv == 0 || !__any_sync(0xffffffffu, rowok)) {
 				if (lane == 0) smask[(pg * NEG + eg) * 2 + h] = 0;
 				if (eg * 32 < bn && lv != 0) {

@@ -158,7 +158,8 @@ template <int RB> struct FwdCfg {
 	static constexpr size_t O_LOC = O_LIVE + 4 * 2 * NPG;
 	static constexpr size_t O_TAIL = (O_LOC + 4 * (LGS_NB + 1) + 15) / 16 * 16; // straggler state: TL x (float4 + uint4)
 	static constexpr int TL = 2 * NW;                     // switch to straggler mode when <= TL pixels of the bin are live
-	static constexpr size_t BYTES = O_TAIL + 32 * TL;
+	static constexpr size_t O_FLAG = O_TAIL + 32 * TL;    // one byte per entry of the chunk: bit (2 * group + row) = "blended in that row"
+	static constexpr size_t BYTES = O_FLAG + LGS_SEG_CAP;
 	// straggler mode stages whole sub-chunks of TSUB entries (100 B each) in the memory of the two alpha tiles
 	static constexpr int TSUB_ = (int)(2 * TILE / 100) / 32 * 32;
 	static constexpr int TSUB = TSUB_ < 256 ? TSUB_ : 256;
@@ -246,6 +247,7 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 	// straggler mode (see below): per-slot pixel state lives in shared memory between segments
 	float4 *ts0 = reinterpret_cast<float4 *>(smem + C::O_TAIL);        // T, C0, C1, D
 	uint4 *ts1 = reinterpret_cast<uint4 *>(smem + C::O_TAIL) + C::TL;  // last, stop, pixel (group * 32 + lane), done
+	unsigned *sflagw = reinterpret_cast<unsigned *>(smem + C::O_FLAG);
 	bool tail = false;
 	int ntail = 0, myslot = -1;
 	bool all_done = false;
@@ -297,6 +299,7 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 				}
 			}
 			if (all_done) continue; // sort_all mode: keep sorting, nothing left to blend
+			for (int i = tid; i < (m + 3) / 4; i += NT) sflagw[i] = 0; // ordered before its first use by the barriers below
 			if (!tail) {
 				// Straggler mode.  Once only a handful of pixels of the bin are still live (rays that found no
 				// dense surface yet), the batch pipeline is all latency: a barrier, a record prefetch and a
@@ -377,6 +380,10 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 								s0v.w = __fmaf_rn(s0v.x, __fmul_rn(al, f.z), s0v.w);
 								s0v.x = test_T;
 								s1.x = posb + g0 + b + 1;
+								if (RB <= 8 && lane == 0) {
+									const int je = sub0 + g0 + b;
+									atomicOr(&sflagw[je >> 2], (1u << (2 * (s1.z >> 5) + ((s1.z >> 4) & 1u))) << (8 * (je & 3)));
+								}
 							}
 						}
 						if (lane == 0) { ts0[slot] = s0v; ts1[slot] = s1; }
@@ -388,6 +395,7 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 					for (int i = 0; i < ntail; i++) alive |= ts1[i].w ^ 1u;
 					all_done = alive == 0;
 				}
+				for (int i = tid; i < m; i += NT) seg[c0 + i].w = RB <= 8 ? (sflagw[i >> 2] >> (8 * (i & 3))) & 0xffu : 0xffffu;
 				if (all_done && !sort_all) break;
 				continue;
 			}
@@ -469,25 +477,33 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 							if (nib == 0) continue;
 							const float4 a4 = *reinterpret_cast<const float4 *>(trow + j0);
 							const float4 f0 = st.feat[j0], f1 = st.feat[j0 + 1], f2 = st.feat[j0 + 2], f3 = st.feat[j0 + 3];
+							unsigned rowf = 0; // per entry of the quad, bits 0/1: blended by a pixel of row 0/1 of this group
 #define LGS_BLEND1(al_, f_, bit_)                                                                  \
-	if ((nib & (1u << bit_)) && al_ != 0.f && !done) {                                         \
-		const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al_));                           \
-		if (test_T < 0.0001f) {                                                            \
-			done = true;                                                               \
-			stop = pos0 + j0 + bit_ + 1;                                               \
-		} else {                                                                           \
-			C0 = __fmaf_rn(T, __fmul_rn(al_, f_.x), C0);                               \
-			C1 = __fmaf_rn(T, __fmul_rn(al_, f_.y), C1);                               \
-			D = __fmaf_rn(T, __fmul_rn(al_, f_.z), D);                                 \
-			T = test_T;                                                                \
-			last = pos0 + j0 + bit_ + 1;                                               \
+	if (nib & (1u << bit_)) {                                                                  \
+		bool bl_ = false;                                                                  \
+		if (al_ != 0.f && !done) {                                                         \
+			const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al_));                   \
+			if (test_T < 0.0001f) {                                                    \
+				done = true;                                                       \
+				stop = pos0 + j0 + bit_ + 1;                                       \
+			} else {                                                                   \
+				C0 = __fmaf_rn(T, __fmul_rn(al_, f_.x), C0);                       \
+				C1 = __fmaf_rn(T, __fmul_rn(al_, f_.y), C1);                       \
+				D = __fmaf_rn(T, __fmul_rn(al_, f_.z), D);                         \
+				T = test_T;                                                        \
+				last = pos0 + j0 + bit_ + 1;                                       \
+				bl_ = true;                                                        \
+			}                                                                          \
 		}                                                                                  \
+		const unsigned bm_ = __ballot_sync(0xffffffffu, bl_);                              \
+		rowf |= (((bm_ & 0xffffu) ? 1u : 0u) | ((bm_ >> 16) ? 2u : 0u)) << (8 * bit_);     \
 	}
 							LGS_BLEND1(a4.x, f0, 0)
 							LGS_BLEND1(a4.y, f1, 1)
 							LGS_BLEND1(a4.z, f2, 2)
 							LGS_BLEND1(a4.w, f3, 3)
 #undef LGS_BLEND1
+							if (RB <= 8 && lane == 0 && rowf) atomicOr(&sflagw[((b - 1) * B + j0) >> 2], rowf << (2 * warp));
 						}
 					}
 					const unsigned lvn = __ballot_sync(0xffffffffu, !done);
@@ -502,6 +518,8 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 				}
 			}
 			gb += nb;
+			// the backward pass skips (entry, row) pairs nothing was blended in: flags ride in the entry's spare word
+			for (int i = tid; i < m; i += NT) seg[c0 + i].w = RB <= 8 ? (sflagw[i >> 2] >> (8 * (i & 3))) & 0xffu : 0xffffu;
 			if (all_done && !sort_all) break;
 		}
 		k = k2;
