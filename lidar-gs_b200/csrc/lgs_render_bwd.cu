@@ -136,7 +136,7 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			const float go = dL_docc[pix];
 			kocc = (go - (bg[0] * g0 + bg[1] * g1)) * Tf; // occ + background terms, both ~ T_final / (1 - alpha)
 		}
-		sray[warp * 32 + lane] = make_float4(ray.x, ray.y, ray.z, 0.f);
+		sray[warp * 32 + lane] = make_float4(ray.x, ray.y, ray.z, __uint_as_float(lastc));
 		sg[warp * 32 + lane] = make_float4(g0, g1, gd, 0.f);
 		slast[warp * 32 + lane] = lastc;
 		unsigned wmax = lastc;
@@ -187,17 +187,16 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			const float4 q0 = st.q[jj], q1 = st.q[B + jj], q2 = st.q[2 * B + jj], q3 = st.q[3 * B + jj];
 			const float4 uu = st.u[jj];
 			float *tcol = tileA + (size_t)(pg * 32 + 16 * h) * LD + j;
-			const float4 *rays = sray + pg * 32 + 16 * h;
-			const unsigned *lasts = slast + pg * 32 + 16 * h;
+			const unsigned rays = lgs_smem_addr(sray + pg * 32 + 16 * h), tcs = lgs_smem_addr(tcol);
 			const unsigned pos = lo + (unsigned)j;
 			float amax = 0.f;
 			while (lv) {
 				const int p = __ffs(lv) - 1;
 				lv &= lv - 1;
-				const float4 rr = rays[p];
+				const float4 rr = lgs_lds128(rays + 16u * p); // .w carries the pixel's last contributor (as bits)
 				float alpha = 0.f;
-				if (rowok && pos < lasts[p]) alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, q0, q1, q2, q3, uu);
-				tcol[p * LD] = alpha;
+				if (rowok && pos < __float_as_uint(rr.w)) alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, q0, q1, q2, q3, uu);
+				lgs_sts32(tcs + (unsigned)(4 * LD) * p, alpha);
 				amax = fmaxf(amax, alpha);
 			}
 			const unsigned m32 = __ballot_sync(0xffffffffu, amax != 0.f);
@@ -265,18 +264,18 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			const float4 uu = st.u[j];
 			const float r11 = uu.z, r22 = uu.w;
 			const float ab = (c.x * d.x + c.y * d.y + c.z * d.z) * r11 * r22; // (u1/|u1|^2) . (u2/|u2|^2)
-			const float *ta = tileA + (size_t)(pg * 32 + 16 * h) * LD + j;
-			const float *tb = tileB + (size_t)(pg * 32 + 16 * h) * LD + j;
-			const float4 *rays = sray + pg * 32 + 16 * h, *gs = sg + pg * 32 + 16 * h;
+			const unsigned ta = lgs_smem_addr(tileA + (size_t)(pg * 32 + 16 * h) * LD + j);
+			const unsigned tb = lgs_smem_addr(tileB + (size_t)(pg * 32 + 16 * h) * LD + j);
+			const unsigned rays = lgs_smem_addr(sray + pg * 32 + 16 * h), gs = lgs_smem_addr(sg + pg * 32 + 16 * h);
 			float sKx = 0.f, sKy = 0.f, sM = 0.f, aXx = 0.f, aXy = 0.f, aXz = 0.f, aXu = 0.f, aYx = 0.f, aYy = 0.f,
 			      aYz = 0.f, aYu = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, opa = 0.f, col0 = 0.f, col1 = 0.f, dep = 0.f;
 			while (lv) {
 				const int p = __ffs(lv) - 1;
 				lv &= lv - 1;
-				const float w = tb[p * LD];
+				const float w = lgs_lds32(tb + (unsigned)(4 * LD) * p);
 				if (w == 0.f) continue;
-				const float dLda = ta[p * LD];
-				const float4 rr = rays[p], gg = gs[p];
+				const float dLda = lgs_lds32(ta + (unsigned)(4 * LD) * p);
+				const float4 rr = lgs_lds128(rays + 16u * p), gg = lgs_lds128(gs + 16u * p);
 				const float ddx = b.x - rr.x, ddy = b.y - rr.y, ddz = b.z - rr.z;
 				const float du1 = ddx * c.x + ddy * c.y + ddz * c.z, du2 = ddx * d.x + ddy * d.y + ddz * d.z;
 				const float dx = du1 * r11, dy = du2 * r22;

@@ -435,15 +435,15 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 						if (lv != 0 && __any_sync(0xffffffffu, rowok)) {
 							const float4 q0 = st.q[jj], q1 = st.q[B + jj], q2 = st.q[2 * B + jj], q3 = st.q[3 * B + jj];
 							const float4 uu = st.u[jj];
-							const float4 *rays = sray + epg * 32 + 16 * eh;
+							const unsigned rays = lgs_smem_addr(sray + epg * 32 + 16 * eh), tcs = lgs_smem_addr(tcol);
 							float amax = 0.f;
 							while (lv) {
 								const int p = __ffs(lv) - 1;
 								lv &= lv - 1;
-								const float4 rr = rays[p];
+								const float4 rr = lgs_lds128(rays + 16u * p);
 								float alpha = 0.f;
 								if (rowok) alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, q0, q1, q2, q3, uu);
-								tcol[p * LD] = alpha;
+								lgs_sts32(tcs + (unsigned)(4 * LD) * p, alpha);
 								amax = fmaxf(amax, alpha);
 							}
 							m32 = __ballot_sync(0xffffffffu, amax != 0.f);
