@@ -100,6 +100,46 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": float(max(pw))}
 
 
+def reference_cuda_timing(sc, anc, iters=20):
+    """Context for the reference arm: the UNMODIFIED reference CUDA rasterizer (oracle/_ref, built from
+    /root/reference by oracle/build_ref.py) on the same step, inputs resident -- reported beside the CPU figure,
+    never as `value`.  None when the build or a GPU is absent."""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        import build_ref
+        import make_goldens as MG
+        ref = build_ref.load()
+        if ref is None:
+            return None
+        dev = torch.device("cuda:0")
+        d = MG.to_dev(sc, dev)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        am, a6, ar = t(anc["means"]), t(anc["scales6"]), t(anc["rots"])
+        empty = torch.Tensor([])
+
+        def step():
+            ref.rasterize_aussians_filter(am, a6[:, :3], ar, 1.0, empty, d["viewmatrix"], d["projmatrix"], d["campos"], 1.0, 1.0,
+                                          int(sc["H"]), int(sc["W"]), d["beams"], False, int(sc["far"]), int(sc["near"]), False)
+            MG.run_ref(ref, sc, dev, d=d)
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        return {"ms_per_step": ms, "frames_per_s": 1e3 / ms, "steps": iters,
+                "note": "reference CUDA source compiled for sm_100a, same cfg3 step (filter+fwd+bwd), inputs resident"}
+    except Exception as e:  # context only: never fail the reference arm on it
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU restatement (oracle/) with all host threads; rank 0 only."""
     if rank != 0:
@@ -124,6 +164,7 @@ def run_reference(args, rank, world):
         step()
     dt = (time.time() - t0) / max(args.steps, 1)
     v = 1.0 / dt
+    extra = {"reference_cuda_sm100a": reference_cuda_timing(sc, anc)}
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -131,7 +172,8 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": "every step = one full cfg3 frame (filter+fwd+bwd) on the CPU restatement "
                                        "oracle/lgs_oracle.c (C + OpenMP); the reference ships no CPU rasterizer"},
-            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "extra": extra}
     print(json.dumps(line), flush=True)
 
 
@@ -372,8 +414,13 @@ def main():
             per[s] = {"ms_per_step": tot_ms / args.steps, "launches_per_step": n / args.steps,
                       "gbs": alg[s] / (tot_ms / args.steps * 1e-3) / 1e9}
     dom = max((s for s in per if s != "clear"), key=lambda s: per[s]["ms_per_step"])
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": per[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": per[dom]["gbs"] / peak, "traffic": None,
+            "frac": per[dom]["gbs"] / peak, "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
             "alg_bytes_per_launch": alg[dom], "avg_launch_ms": per[dom]["ms_per_step"] / max(per[dom]["launches_per_step"], 1)}
     frame_bytes = 124.0 * P + 276.0 * V + 164.0 * R + 48.0 * HW  # SURVEY.md §8d full-sort byte model

@@ -64,8 +64,10 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user,
  * geom/binning/image buffers are the ones lgs_forward() filled.  The reference's five
  * intermediate gradient arrays (dL_dconic, dL_ddepths, dL_dsphere_means3D, dL_dbasis_u1/u2 --
  * rasterize_points.cu:163-175) are replaced by ONE packed scratch `grad_scratch` of
- * lgs_backward_scratch_bytes(P) bytes that the library zeroes itself.  Every output is fully
- * written (no pre-zeroing): dL_dmean2D[P,4], dL_dopacity[P], dL_dcolor[P,2], dL_dmean3D[P,3],
+ * lgs_backward_scratch_bytes(P) bytes (a [P,20] accumulator, a one-bit-per-Gaussian "touched" mask
+ * and the list of touched Gaussians) that the library initialises itself: only the rows of
+ * Gaussians the replayed list prefixes refer to are zeroed.  Every output is fully written (no
+ * pre-zeroing by the caller; untouched Gaussians get zeros by memset): dL_dmean2D[P,4], dL_dopacity[P], dL_dcolor[P,2], dL_dmean3D[P,3],
  * dL_dcov3D[P,6] (may be NULL), dL_dscale[P,3] and dL_drot[P,4] (NULL iff cov3D_precomp given).
  * dL_dsh is accepted and untouched (M == 0 on this path).
  */
@@ -119,13 +121,13 @@ long long lgs_last_num_instances(void);
  * ms_per_stage / launches_per_stage are arrays of LGS_NUM_STAGES entries (sums since enable).
  */
 enum {
-	LGS_STAGE_CLEAR = 0,    /* memsets: bucket counters, gradient accumulator */
+	LGS_STAGE_CLEAR = 0,    /* memsets (bucket counters, touched mask, zero-fill of the API gradients) + the mark kernel */
 	LGS_STAGE_PROJECT = 1,  /* per-Gaussian projection + record packing + bucket counting */
 	LGS_STAGE_SCAN = 2,     /* bucket counts -> offsets (2 launches) */
 	LGS_STAGE_SCATTER = 3,  /* (Gaussian, bin) instances -> depth-bucketed lists */
 	LGS_STAGE_RENDER_FWD = 4, /* lazy per-bin sort + front-to-back compositing */
-	LGS_STAGE_RENDER_BWD = 5, /* back-to-front gradient pass */
-	LGS_STAGE_FINALIZE_BWD = 6, /* per-Gaussian chain rule, writes all API grads */
+	LGS_STAGE_RENDER_BWD = 5, /* gradient pass over the sorted list prefixes */
+	LGS_STAGE_FINALIZE_BWD = 6, /* per-Gaussian chain rule for the touched Gaussians */
 	LGS_STAGE_FILTER = 7,   /* anchor visibility pre-filter */
 	LGS_NUM_STAGES = 8
 };

@@ -109,27 +109,46 @@ scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__rest
 	}
 }
 
-// One thread per Gaussian (x-span x row-group-span instances each, ~3 on average).
+// One thread per Gaussian; a Gaussian with a large footprint (near range: hundreds of bins) is expanded by its
+// whole warp, so no lane serialises a long loop while 31 others wait.
+#define LGS_COOP_MIN 12
 __global__ void __launch_bounds__(256)
 scatter_kernel(int P, int gx, int RB, const uint4 *__restrict__ aux, uint32_t *__restrict__ cursor,
 	       const uint32_t *__restrict__ loc, const uint32_t *__restrict__ binbase, uint4 *__restrict__ entries,
 	       unsigned capacity, FrameTotals *__restrict__ totals)
 {
-	int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= P) return;
-	uint4 a = aux[idx];
-	int x0 = a.x & 0xffff, x1 = a.x >> 16, y0 = a.y & 0xffff, y1 = a.y >> 16;
-	if (x1 <= x0) return;
-	unsigned bucket = a.w;
-	uint4 e = make_uint4(a.z, (unsigned)idx, a.y, 0u);
-	int g0 = y0 / RB, g1 = (y1 - 1) / RB;
-	for (int g = g0; g <= g1; g++)
-		for (int x = x0; x < x1; x++) {
-			size_t bb = (size_t)(g * gx + x) * LGS_NB + bucket;
-			unsigned pos = binbase[g * gx + x] + loc[bb] + atomicAdd(&cursor[bb], 1u);
-			if (pos < capacity) entries[pos] = e;
-			else atomicAdd(&totals->overflow, 1u);
-		}
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+	uint4 a = make_uint4(0, 0, 0, 0);
+	if (idx < P) a = aux[idx];
+	int x0 = a.x & 0xffff, nx = (int)(a.x >> 16) - x0, y0 = a.y & 0xffff, y1 = a.y >> 16;
+	int g0 = y0 / RB, ng = nx > 0 ? (y1 - 1) / RB - g0 + 1 : 0;
+	int n = nx > 0 ? nx * ng : 0;
+	unsigned overflow = 0;
+	auto emit = [&](int x0_, int nx_, int g0_, unsigned bucket, const uint4 &e, int i) {
+		const int g = g0_ + i / nx_, x = x0_ + i - (i / nx_) * nx_;
+		const size_t bb = (size_t)(g * gx + x) * LGS_NB + bucket;
+		const unsigned pos = binbase[g * gx + x] + loc[bb] + atomicAdd(&cursor[bb], 1u);
+		if (pos < capacity) entries[pos] = e;
+		else overflow++;
+	};
+	const uint4 e = make_uint4(a.z, (unsigned)idx, a.y, 0u);
+	if (n < LGS_COOP_MIN) {
+#pragma unroll 4
+		for (int i = 0; i < n; i++) emit(x0, nx, g0, a.w, e, i);
+	}
+	unsigned big = __ballot_sync(0xffffffffu, n >= LGS_COOP_MIN);
+	while (big) {
+		const int src = __ffs(big) - 1;
+		big &= big - 1;
+		const int sx0 = __shfl_sync(0xffffffffu, x0, src), snx = __shfl_sync(0xffffffffu, nx, src);
+		const int sg0 = __shfl_sync(0xffffffffu, g0, src), sn = __shfl_sync(0xffffffffu, n, src);
+		const unsigned sb = __shfl_sync(0xffffffffu, a.w, src);
+		uint4 se;
+		se.x = __shfl_sync(0xffffffffu, e.x, src); se.y = __shfl_sync(0xffffffffu, e.y, src);
+		se.z = __shfl_sync(0xffffffffu, e.z, src); se.w = 0u;
+		for (int i = lane; i < sn; i += 32) emit(sx0, snx, sg0, sb, se, i);
+	}
+	if (overflow) atomicAdd(&totals->overflow, overflow);
 }
 
 } // namespace

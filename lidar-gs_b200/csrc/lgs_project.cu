@@ -40,8 +40,8 @@ __device__ __forceinline__ bool project_gaussian(int idx, const float *__restric
 						 const float *__restrict__ rotations,
 						 const float *__restrict__ cov3D_precomp,
 						 const float *__restrict__ view, int W, int H,
-						 const float *__restrict__ beams, int far_, int near_, int gx, int gy,
-						 Projected &o)
+						 const float *__restrict__ beams, const float *__restrict__ tanrow, float tanW,
+						 int far_, int near_, int gx, int gy, Projected &o)
 {
 	const float pi = 3.14159265358979323846f;
 	const float Ray_Divergence_Angle = 0.002f;
@@ -132,8 +132,11 @@ __device__ __forceinline__ bool project_gaussian(int idx, const float *__restric
 		if (alpha < (before - Ray_Divergence_Angle * 2)) return false;
 	}
 	p_r = H - p_r - 1;
-	int my_radius_y = ceil(3.f * my_radius / tan(abs(after - before)));
-	int my_radius_x = ceil(3.f * my_radius / tan(2 * pi / W));
+	// tan(|b[i] - b[i-1]|) and tan(2 pi / W) depend on the beam row / the frame only: tabulated once per block
+	// (same tanf, same argument => same bits as the reference's per-Gaussian evaluation, fwd.cu:361-362)
+	const float trow = tanrow ? tanrow[p_r_int] : tan(abs(after - before));
+	int my_radius_y = ceil(3.f * my_radius / trow);
+	int my_radius_x = ceil(3.f * my_radius / tanW);
 
 	// tile rect (aux.h:80-92), BLOCK_X = 16, BLOCK_Y = 1
 	int x0 = min(gx, max((int)0, (int)((p_c - my_radius_x) / LGS_TILE_X_)));
@@ -160,6 +163,28 @@ __device__ __forceinline__ int depth_bucket(float depth, int far_, int near_)
 	return min(LGS_NB - 1, max(0, b));
 }
 
+// beam table + per-row tangents in shared memory (falls back to the global table when H is too large)
+#define LGS_MAX_SMEM_ROWS 2048
+__device__ __forceinline__ void load_beam_tables(const float *__restrict__ beams, int H, int W, float *sb, float *st,
+						 const float *&b_out, const float *&t_out, float &tanW)
+{
+	const float pi = 3.14159265358979323846f;
+	tanW = tan(2 * pi / W);
+	if (H <= LGS_MAX_SMEM_ROWS) {
+		for (int i = threadIdx.x; i < H; i += blockDim.x) {
+			const float after = beams[i > 0 ? i : 1], before = beams[i > 0 ? i - 1 : 0];
+			sb[i] = beams[i];
+			st[i] = tan(abs(after - before));
+		}
+		__syncthreads();
+		b_out = sb;
+		t_out = st;
+	} else {
+		b_out = beams;
+		t_out = nullptr;
+	}
+}
+
 __global__ void __launch_bounds__(256)
 project_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ scales, float mod,
 	       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
@@ -169,15 +194,21 @@ project_kernel(int P, const float *__restrict__ means3D, const float *__restrict
 	       float4 *__restrict__ rec, uint4 *__restrict__ aux, int *__restrict__ radii,
 	       int *__restrict__ radii_xy, uint32_t *__restrict__ cnt, FrameTotals *__restrict__ totals)
 {
+	extern __shared__ float stab[];
+	const float *bt, *tt;
+	float tanW;
+	load_beam_tables(beams, H, W, stab, stab + H, bt, tt, tanW);
 	int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned tiles = 0, vis = 0;
+	int cx0 = 0, cnx = 1, cg0 = 0, cn = 0, cbucket = 0; // (bin, bucket) instances of this Gaussian to count
 	if (idx < P) {
+		// issue the loads that are only needed at the end now, so their latency hides behind the projection math
+		const float o = opacities[idx];
+		const float2 f = *reinterpret_cast<const float2 *>(colors + 2 * (size_t)idx);
 		Projected pj;
-		bool ok = project_gaussian<false>(idx, means3D, scales, mod, rotations, cov3D_precomp, view, W, H, beams,
+		bool ok = project_gaussian<false>(idx, means3D, scales, mod, rotations, cov3D_precomp, view, W, H, bt, tt, tanW,
 						  far_, near_, gx, H, pj);
 		if (ok) {
-			float o = opacities[idx];
-			float2 f = *reinterpret_cast<const float2 *>(colors + 2 * (size_t)idx);
 			float4 *r = rec + 4 * (size_t)idx;
 			r[0] = make_float4(pj.conic.x, pj.conic.y, pj.conic.z, o);
 			r[1] = make_float4(pj.s.x, pj.s.y, pj.s.z, pj.depth);
@@ -193,10 +224,9 @@ project_kernel(int P, const float *__restrict__ means3D, const float *__restrict
 			}
 			tiles = (unsigned)((pj.x1 - pj.x0) * (pj.y1 - pj.y0));
 			vis = 1;
-			int g0 = pj.y0 / RB, g1 = (pj.y1 - 1) / RB;
-			for (int g = g0; g <= g1; g++)
-				for (int x = pj.x0; x < pj.x1; x++)
-					atomicAdd(&cnt[(size_t)(g * gx + x) * LGS_NB + bucket], 1u);
+			cx0 = pj.x0; cnx = pj.x1 - pj.x0; cg0 = pj.y0 / RB;
+			cn = cnx * ((pj.y1 - 1) / RB - cg0 + 1);
+			cbucket = bucket;
 		} else {
 			aux[idx] = make_uint4(0, 0, 0, 0);
 			radii[idx] = 0;
@@ -204,6 +234,24 @@ project_kernel(int P, const float *__restrict__ means3D, const float *__restrict
 				radii_xy[2 * idx] = 0;
 				radii_xy[2 * idx + 1] = 0;
 			}
+		}
+	}
+	// count the (bin, depth bucket) instances; large footprints are expanded by the whole warp
+	{
+		const int lane = threadIdx.x & 31;
+		if (cn < 12) {
+			for (int i = 0; i < cn; i++)
+				atomicAdd(&cnt[(size_t)((cg0 + i / cnx) * gx + cx0 + i % cnx) * LGS_NB + cbucket], 1u);
+		}
+		unsigned big = __ballot_sync(0xffffffffu, cn >= 12);
+		while (big) {
+			const int src = __ffs(big) - 1;
+			big &= big - 1;
+			const int sx0 = __shfl_sync(0xffffffffu, cx0, src), snx = __shfl_sync(0xffffffffu, cnx, src);
+			const int sg0 = __shfl_sync(0xffffffffu, cg0, src), sn = __shfl_sync(0xffffffffu, cn, src);
+			const int sb = __shfl_sync(0xffffffffu, cbucket, src);
+			for (int i = lane; i < sn; i += 32)
+				atomicAdd(&cnt[(size_t)((sg0 + i / snx) * gx + sx0 + i % snx) * LGS_NB + sb], 1u);
 		}
 	}
 	// block-level totals: one atomic per warp
@@ -225,10 +273,14 @@ filter_kernel(int P, const float *__restrict__ means3D, const float *__restrict_
 	      const float *__restrict__ view, int W, int H, const float *__restrict__ beams, int far_, int near_,
 	      int gx, int *__restrict__ radii, int *__restrict__ radii_xy)
 {
+	extern __shared__ float stab[];
+	const float *bt, *tt;
+	float tanW;
+	load_beam_tables(beams, H, W, stab, stab + H, bt, tt, tanW);
 	int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= P) return;
 	Projected pj;
-	bool ok = project_gaussian<true>(idx, means3D, scales, mod, rotations, cov3D_precomp, view, W, H, beams, far_,
+	bool ok = project_gaussian<true>(idx, means3D, scales, mod, rotations, cov3D_precomp, view, W, H, bt, tt, tanW, far_,
 					 near_, gx, H, pj);
 	radii[idx] = ok ? max(pj.rx, pj.ry) : 0;
 	if (radii_xy) {
@@ -254,7 +306,8 @@ void lgs_launch_project(const FrameGeom &g, const float *means3D, const float *s
 			const float *colors, const float *view, const float *beams, int far_, int near_,
 			const GeomPtrs &gp, int *radii, int *radii_xy, cudaStream_t st)
 {
-	project_kernel<<<(g.P + 255) / 256, 256, 0, st>>>(g.P, means3D, scales, mod, rotations, cov3D_precomp, opacities,
+	const size_t tab = g.H <= LGS_MAX_SMEM_ROWS ? 8 * (size_t)g.H : 0;
+	project_kernel<<<(g.P + 255) / 256, 256, tab, st>>>(g.P, means3D, scales, mod, rotations, cov3D_precomp, opacities,
 							  colors, view, g.W, g.H, beams, far_, near_, g.gx, g.RB, gp.rec,
 							  gp.aux, radii, radii_xy, gp.cnt, gp.totals);
 }
@@ -264,7 +317,8 @@ void lgs_launch_filter(int P, const float *means3D, const float *scales, float m
 		       int near_, int *radii, int *radii_xy, cudaStream_t st)
 {
 	int gx = (W + LGS_TILE_X_ - 1) / LGS_TILE_X_;
-	filter_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, scales, mod, rotations, cov3D_precomp, view, W, H, beams,
+	const size_t tab = H <= LGS_MAX_SMEM_ROWS ? 8 * (size_t)H : 0;
+	filter_kernel<<<(P + 255) / 256, 256, tab, st>>>(P, means3D, scales, mod, rotations, cov3D_precomp, view, W, H, beams,
 						       far_, near_, gx, radii, radii_xy);
 }
 
