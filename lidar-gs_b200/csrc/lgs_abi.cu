@@ -17,6 +17,10 @@ thread_local char g_err[512] = "";
 thread_local FrameTotals *g_pinned = nullptr;     // mapped pinned host memory the scan kernel writes the frame totals into
 thread_local FrameTotals *g_pinned_dev = nullptr; // its device-side address
 thread_local long long g_last_instances = 0;
+// side stream for work that is independent of the main dependency chain (zero-fill of the API gradients while the
+// gradient kernel runs); forked from and joined back into the caller's stream with events
+thread_local cudaStream_t g_side = nullptr;
+thread_local cudaEvent_t g_fork = nullptr, g_join = nullptr;
 std::atomic<int> g_rows_per_bin{0};
 std::atomic<int> g_sort_all{0};
 std::atomic<long long> g_launches{0};
@@ -204,19 +208,29 @@ int lgs_backward(int P, int D, int M, int R, const float *background, int width,
 	uint32_t *tlist = (uint32_t *)((char *)touched + touched_bytes(P)); // ids of touched Gaussians; length at touched[(P+31)/32]
 	CK(cudaMemsetAsync(touched, 0, touched_bytes(P), st));
 	lgs_launch_mark_touched(g, gp, ip, (const uint4 *)binning_buffer, grad_scratch, touched, tlist, st);
-	// every API gradient of an untouched Gaussian is zero: plain memsets, the finalize kernel only visits the list
-	CK(cudaMemsetAsync(dL_dmean2D, 0, (size_t)P * 16, st));
-	CK(cudaMemsetAsync(dL_dopacity, 0, (size_t)P * 4, st));
-	CK(cudaMemsetAsync(dL_dcolor, 0, (size_t)P * 8, st));
-	CK(cudaMemsetAsync(dL_dmean3D, 0, (size_t)P * 12, st));
-	if (dL_dcov3D) CK(cudaMemsetAsync(dL_dcov3D, 0, (size_t)P * 24, st));
-	if (dL_dscale) CK(cudaMemsetAsync(dL_dscale, 0, (size_t)P * 12, st));
-	if (dL_drot) CK(cudaMemsetAsync(dL_drot, 0, (size_t)P * 16, st));
 	g_timer.end(st);
+	// every API gradient of an untouched Gaussian is zero: plain memsets, issued on a side stream so that they
+	// overlap the (compute-bound) gradient kernel; the finalize kernel, which only visits the list, waits for them
+	if (!g_side) {
+		CK(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
+	}
+	CK(cudaEventRecord(g_fork, st));
+	CK(cudaStreamWaitEvent(g_side, g_fork, 0));
+	CK(cudaMemsetAsync(dL_dmean2D, 0, (size_t)P * 16, g_side));
+	CK(cudaMemsetAsync(dL_dopacity, 0, (size_t)P * 4, g_side));
+	CK(cudaMemsetAsync(dL_dcolor, 0, (size_t)P * 8, g_side));
+	CK(cudaMemsetAsync(dL_dmean3D, 0, (size_t)P * 12, g_side));
+	if (dL_dcov3D) CK(cudaMemsetAsync(dL_dcov3D, 0, (size_t)P * 24, g_side));
+	if (dL_dscale) CK(cudaMemsetAsync(dL_dscale, 0, (size_t)P * 12, g_side));
+	if (dL_drot) CK(cudaMemsetAsync(dL_drot, 0, (size_t)P * 16, g_side));
+	CK(cudaEventRecord(g_join, g_side));
 	g_timer.begin(LGS_STAGE_RENDER_BWD, st);
 	lgs_launch_render_bwd(g, gp, ip, (const uint4 *)binning_buffer, background, beam_inclinations, dL_dpix,
 			      dL_dout_depth, dL_dout_occ, grad_scratch, st);
 	g_timer.end(st);
+	CK(cudaStreamWaitEvent(st, g_join, 0));
 	g_timer.begin(LGS_STAGE_FINALIZE_BWD, st);
 	lgs_launch_finalize_bwd(g, means3D, scales, scale_modifier, rotations, cov3D_precomp, viewmatrix, radii,
 				grad_scratch, touched, tlist, dL_dmean2D, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dscale, dL_drot,
