@@ -107,6 +107,66 @@ int lgs_visible_filter(int P, int M, int width, int height,
 int lgs_mark_visible(int P, const float *means3D, const float *viewmatrix,
                      const float *projmatrix, unsigned char *present, void *stream);
 
+/* ==== surfel path (BASELINE config 5) ====================================================
+ * Drop-in for CudaRasterizer::Rasterizer of the reference's SECOND rasterizer,
+ * submodules/diff_lidargs_surfel_rasterization ("RS/", cuda_rasterizer/rasterizer.h:24-117): planar discs
+ * (scales[P,2]), per-pixel ray-disc intersection, outputs colour [2,H,W] + others [7,H,W]
+ * (depth, alpha, normal x3, median depth, distortion; RS auxiliary.h:23-27).  Same conventions as above.
+ */
+
+/*
+ * Replaces RS Rasterizer::forward (rasterizer.h:31-60; rasterizer_impl.cu:200-353).  transMat_precomp must be NULL
+ * (the reference's projection ignores it and its backward rejects it, RS backward.cu:661).  `pixels` [P] may be
+ * NULL; it is zero-filled like the reference leaves it (RS forward.cu:522).  Returns num_rendered or < 0.
+ */
+int lgs_surfel_forward(lgs_alloc_fn geometry_buffer, void *geometry_user,
+                       lgs_alloc_fn binning_buffer, void *binning_user,
+                       lgs_alloc_fn image_buffer, void *image_user,
+                       int P, int D, int M,
+                       const float *background, int width, int height,
+                       const float *means3D, const float *shs, const float *colors_precomp,
+                       const float *opacities, const float *scales, float scale_modifier,
+                       const float *rotations, const float *transMat_precomp,
+                       const float *viewmatrix, const float *projmatrix, const float *cam_pos,
+                       const float *beam_inclinations, int prefiltered, int far, int near,
+                       float *out_color, float *out_others, float *pixels,
+                       int *radii, int *radii_xy, int debug, void *stream);
+
+/*
+ * Replaces RS Rasterizer::backward (rasterizer.h:86-117; rasterizer_impl.cu:357-461).  The reference's
+ * intermediate arrays dL_dnormal[P,3] and dL_dtransMat_2dtemp[P,3] (RS rasterize_points.cu:194-204) are replaced
+ * by ONE packed scratch of lgs_surfel_backward_scratch_bytes(P) bytes which the library zero-fills itself.
+ * Every output is fully written: dL_dmean2D[P,4], dL_dopacity[P], dL_dcolor[P,2], dL_dmean3D[P,3],
+ * dL_dtransMat[P,9] (may be NULL), dL_dscale[P,2], dL_drot[P,4], gs_depth[P] (may be NULL).
+ */
+int lgs_surfel_backward(int P, int D, int M, int R,
+                        const float *background, int width, int height,
+                        const float *means3D, const float *shs, const float *colors_precomp,
+                        const float *scales, float scale_modifier, const float *rotations,
+                        const float *transMat_precomp, const float *viewmatrix, const float *projmatrix,
+                        const float *campos, const float *beam_inclinations, const int *radii,
+                        char *geom_buffer, char *binning_buffer, char *image_buffer,
+                        const float *dL_dpix, const float *dL_dout_others,
+                        float *grad_scratch,
+                        float *dL_dmean2D, float *dL_dopacity, float *dL_dcolor, float *dL_dmean3D,
+                        float *dL_dtransMat, float *dL_dsh, float *dL_dscale, float *dL_drot,
+                        float *gs_depth, int debug, void *stream);
+
+size_t lgs_surfel_backward_scratch_bytes(int P);
+
+/* Replaces RS Rasterizer::visible_filter (rasterizer.h:62-80; rasterizer_impl.cu:464-519 -> forward.cu:551-631). */
+int lgs_surfel_visible_filter(int P, int M, int width, int height,
+                              const float *means3D, const float *scales, float scale_modifier,
+                              const float *rotations, const float *transMat_precomp,
+                              const float *viewmatrix, const float *projmatrix,
+                              const float *beam_inclinations, int prefiltered, int far, int near,
+                              int *radii, int *radii_xy, int debug, void *stream);
+
+/* Replaces RS Rasterizer::markVisible (rasterizer.h:24-29; auxiliary.h:219-246): azimuth of the view-space
+ * point in the (x, z) plane within +-1.658 rad. */
+int lgs_surfel_mark_visible(int P, const float *means3D, const float *viewmatrix,
+                            const float *projmatrix, unsigned char *present, void *stream);
+
 /* ---- knobs and introspection (no reference counterpart) -------------------------------- */
 
 /* Rows of 16x1 tiles that share one depth-binned list (1, 2, 4, 8 or 16; 0 = auto). */

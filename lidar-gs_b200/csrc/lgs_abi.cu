@@ -278,6 +278,165 @@ int lgs_mark_visible(int P, const float *means3D, const float *viewmatrix, const
 	return 0;
 }
 
+// ---- surfel path: mirrors CudaRasterizer::Rasterizer of submodules/diff_lidargs_surfel_rasterization ------------------
+// (RS cuda_rasterizer/rasterizer.h; rasterizer_impl.cu:200-353 forward, :357-461 backward, :464-519 visible_filter,
+// :143-155 markVisible)
+
+int lgs_surfel_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn binning_buffer, void *binning_user,
+		       lgs_alloc_fn image_buffer, void *image_user, int P, int D, int M, const float *background, int width,
+		       int height, const float *means3D, const float *shs, const float *colors_precomp, const float *opacities,
+		       const float *scales, float scale_modifier, const float *rotations, const float *transMat_precomp,
+		       const float *viewmatrix, const float *projmatrix, const float *cam_pos, const float *beam_inclinations,
+		       int prefiltered, int far, int near, float *out_color, float *out_others, float *pixels, int *radii,
+		       int *radii_xy, int debug, void *stream)
+{
+	(void)D; (void)M; (void)shs; (void)projmatrix; (void)cam_pos; (void)prefiltered;
+	cudaStream_t st = (cudaStream_t)stream;
+	g_last_instances = 0;
+	if (P < 0 || width <= 0 || height <= 0) return fail(LGS_EINVAL, "lgs_surfel_forward: bad P / width / height");
+	if (width > 16 * 65535 || height > 65535) return fail(LGS_EINVAL, "lgs_surfel_forward: image too large for the packed rect");
+	if (!out_color || !out_others) return fail(LGS_EINVAL, "lgs_surfel_forward: null output image");
+	const size_t HW = (size_t)width * height;
+	if (pixels && P > 0) CK(cudaMemsetAsync(pixels, 0, (size_t)P * 4, st)); // never written by the reference (fwd.cu:522 is commented out)
+	if (P == 0) { // rasterize_points.cu:88-104: zero images, R = 0
+		CK(cudaMemsetAsync(out_color, 0, HW * LGS_NUM_CHANNELS * 4, st));
+		CK(cudaMemsetAsync(out_others, 0, HW * 7 * 4, st));
+		return 0;
+	}
+	if (!colors_precomp) // rasterizer_impl.cu:246-249
+		return fail(LGS_EINVAL, "For non-RGB, provide precomputed Gaussian colors!");
+	if (transMat_precomp) return fail(LGS_EINVAL, "lgs_surfel_forward: transMat_precomp is not supported (the reference's projection ignores it and its backward rejects it, bwd.cu:661)");
+	if (!means3D || !opacities || !viewmatrix || !beam_inclinations || !background || !radii || !scales || !rotations)
+		return fail(LGS_EINVAL, "lgs_surfel_forward: null input");
+	if (far <= near) return fail(LGS_EINVAL, "lgs_surfel_forward: far <= near");
+	if (height < 2) return fail(LGS_EINVAL, "lgs_surfel_forward: beam table needs >= 2 rows");
+
+	FrameGeom g = make_geom(P, width, height);
+	if (g.RB > 8) { g.RB = 8; g.nrg = (height + 7) / 8; g.nbins = g.gx * g.nrg; }
+	GeomPtrs gsz = lgs_carve_geom(nullptr, g, 16 * LGS_SREC);
+	char *gb = geometry_buffer(gsz.bytes, geometry_user);
+	SurfelImagePtrs isz = lgs_carve_surfel_image(nullptr, g);
+	char *ib = image_buffer(isz.bytes, image_user);
+	if (!gb || !ib) return fail(LGS_ENOMEM, "lgs_surfel_forward: scratch callback returned NULL");
+	GeomPtrs gp = lgs_carve_geom(gb, g, 16 * LGS_SREC);
+	SurfelImagePtrs ip = lgs_carve_surfel_image(ib, g);
+	if (!g_pinned) {
+		CK(cudaHostAlloc((void **)&g_pinned, sizeof(FrameTotals), cudaHostAllocMapped));
+		CK(cudaHostGetDevicePointer((void **)&g_pinned_dev, g_pinned, 0));
+	}
+	g_timer.begin(LGS_STAGE_CLEAR, st);
+	CK(cudaMemsetAsync(gp.cnt, 0, (size_t)g.nbins * LGS_NB * 4, st));
+	CK(cudaMemsetAsync(gp.totals, 0, sizeof(FrameTotals), st));
+	g_timer.end(st);
+	g_timer.begin(LGS_STAGE_PROJECT, st);
+	lgs_launch_surfel_project(g, means3D, scales, scale_modifier, rotations, opacities, colors_precomp, viewmatrix,
+				  beam_inclinations, far, near, gp, radii, radii_xy, st);
+	g_timer.end(st);
+	g_timer.begin(LGS_STAGE_SCAN, st);
+	lgs_launch_scan(g, gp, g_pinned_dev, st);
+	g_timer.end(st);
+	g_launches += 3;
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(st)); // the binning callback needs the instance count (see lgs_forward)
+	const unsigned N = g_pinned->num_instances;
+	const unsigned long long R = g_pinned->num_rendered;
+	g_last_instances = N;
+	if (R > 0x7fffffffULL) return fail(LGS_EINVAL, "lgs_surfel_forward: num_rendered overflows int");
+	char *bb = binning_buffer((size_t)(N ? N : 1) * sizeof(uint4), binning_user);
+	if (!bb) return fail(LGS_ENOMEM, "lgs_surfel_forward: binning callback returned NULL");
+	uint4 *entries = (uint4 *)bb;
+	if (N) {
+		g_timer.begin(LGS_STAGE_SCATTER, st);
+		lgs_launch_scatter(g, gp, entries, N, st);
+		g_timer.end(st);
+		g_launches += 1;
+	}
+	g_timer.begin(LGS_STAGE_RENDER_FWD, st);
+	lgs_launch_surfel_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_others, g_sort_all.load(), st);
+	g_timer.end(st);
+	g_launches += 1;
+	CK(cudaGetLastError());
+	if (debug) CK(cudaStreamSynchronize(st));
+	return (int)R;
+}
+
+size_t lgs_surfel_backward_scratch_bytes(int P) { return lgs_al((size_t)(P > 0 ? P : 1) * LGS_GRAD_STRIDE * sizeof(float)); }
+
+int lgs_surfel_backward(int P, int D, int M, int R, const float *background, int width, int height, const float *means3D,
+			const float *shs, const float *colors_precomp, const float *scales, float scale_modifier,
+			const float *rotations, const float *transMat_precomp, const float *viewmatrix, const float *projmatrix,
+			const float *campos, const float *beam_inclinations, const int *radii, char *geom_buffer,
+			char *binning_buffer, char *image_buffer, const float *dL_dpix, const float *dL_dout_others,
+			float *grad_scratch, float *dL_dmean2D, float *dL_dopacity, float *dL_dcolor, float *dL_dmean3D,
+			float *dL_dtransMat, float *dL_dsh, float *dL_dscale, float *dL_drot, float *gs_depth, int debug, void *stream)
+{
+	(void)D; (void)M; (void)R; (void)shs; (void)colors_precomp; (void)scale_modifier; (void)projmatrix; (void)campos; (void)dL_dsh;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (P < 0 || width <= 0 || height <= 0) return fail(LGS_EINVAL, "lgs_surfel_backward: bad P / width / height");
+	if (P == 0) return 0;
+	if (transMat_precomp) return fail(LGS_EINVAL, "lgs_surfel_backward: transMat_precomp is not supported (bwd.cu:661)");
+	if (!geom_buffer || !binning_buffer || !image_buffer || !grad_scratch)
+		return fail(LGS_EINVAL, "lgs_surfel_backward: null scratch buffer");
+	if (!dL_dpix || !dL_dout_others) return fail(LGS_EINVAL, "lgs_surfel_backward: null upstream gradient");
+	if (!dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dscale || !dL_drot)
+		return fail(LGS_EINVAL, "lgs_surfel_backward: null output");
+	if (!means3D || !viewmatrix || !beam_inclinations || !background || !radii || !scales || !rotations)
+		return fail(LGS_EINVAL, "lgs_surfel_backward: null input");
+	FrameGeom g = make_geom(P, width, height);
+	if (g.RB > 8) { g.RB = 8; g.nrg = (height + 7) / 8; g.nbins = g.gx * g.nrg; }
+	GeomPtrs gp = lgs_carve_geom(geom_buffer, g, 16 * LGS_SREC);
+	SurfelImagePtrs ip = lgs_carve_surfel_image(image_buffer, g);
+	g_timer.begin(LGS_STAGE_CLEAR, st);
+	CK(cudaMemsetAsync(grad_scratch, 0, (size_t)P * LGS_GRAD_STRIDE * sizeof(float), st));
+	g_timer.end(st);
+	g_timer.begin(LGS_STAGE_RENDER_BWD, st);
+	lgs_launch_surfel_render_bwd(g, gp, ip, (const uint4 *)binning_buffer, background, beam_inclinations, dL_dpix,
+				     dL_dout_others, grad_scratch, st);
+	g_timer.end(st);
+	g_timer.begin(LGS_STAGE_FINALIZE_BWD, st);
+	lgs_launch_surfel_finalize_bwd(P, means3D, scales, rotations, viewmatrix, radii, grad_scratch, dL_dmean2D, dL_dopacity,
+				       dL_dcolor, dL_dmean3D, dL_dtransMat, dL_dscale, dL_drot, gs_depth, st);
+	g_timer.end(st);
+	g_launches += 2;
+	CK(cudaGetLastError());
+	if (debug) CK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+int lgs_surfel_visible_filter(int P, int M, int width, int height, const float *means3D, const float *scales,
+			      float scale_modifier, const float *rotations, const float *transMat_precomp, const float *viewmatrix,
+			      const float *projmatrix, const float *beam_inclinations, int prefiltered, int far, int near, int *radii,
+			      int *radii_xy, int debug, void *stream)
+{
+	(void)M; (void)projmatrix; (void)prefiltered; (void)transMat_precomp;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (P < 0 || width <= 0 || height < 2) return fail(LGS_EINVAL, "lgs_surfel_visible_filter: bad P / width / height");
+	if (P == 0) return 0;
+	if (!means3D || !viewmatrix || !beam_inclinations || !radii || !scales || !rotations)
+		return fail(LGS_EINVAL, "lgs_surfel_visible_filter: null input");
+	g_timer.begin(LGS_STAGE_FILTER, st);
+	lgs_launch_surfel_filter(P, means3D, scales, scale_modifier, rotations, viewmatrix, width, height, beam_inclinations, far, near,
+				 radii, radii_xy, st);
+	g_timer.end(st);
+	g_launches += 1;
+	CK(cudaGetLastError());
+	if (debug) CK(cudaStreamSynchronize(st));
+	return 0;
+}
+
+int lgs_surfel_mark_visible(int P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+			    unsigned char *present, void *stream)
+{
+	(void)projmatrix;
+	if (P < 0) return fail(LGS_EINVAL, "lgs_surfel_mark_visible: bad P");
+	if (P == 0) return 0;
+	if (!means3D || !viewmatrix || !present) return fail(LGS_EINVAL, "lgs_surfel_mark_visible: null input");
+	lgs_launch_surfel_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+	g_launches += 1;
+	CK(cudaGetLastError());
+	return 0;
+}
+
 int lgs_set_rows_per_bin(int rows)
 {
 	if (rows != 0 && rows != 1 && rows != 2 && rows != 4 && rows != 8 && rows != 16)

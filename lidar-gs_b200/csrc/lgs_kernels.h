@@ -32,3 +32,23 @@ void lgs_launch_finalize_bwd(const FrameGeom &g, const float *means3D, const flo
 			     const float *rotations, const float *cov3D_precomp, const float *view, const int *radii,
 			     const float *grad, const uint32_t *touched, const uint32_t *tlist, float *dL_dmean2D, float *dL_dopacity, float *dL_dcolor,
 			     float *dL_dmean3D, float *dL_dcov3D, float *dL_dscale, float *dL_drot, cudaStream_t st);
+
+// ---- surfel path (lgs_surfel_project.cu, lgs_surfel_render.cu) -------------------------------------------------------
+#include "lgs_surfel.cuh"
+void lgs_launch_surfel_project(const FrameGeom &g, const float *means3D, const float *scales, float mod, const float *rotations,
+			       const float *opacities, const float *colors, const float *view, const float *beams, int far_,
+			       int near_, const GeomPtrs &gp, int *radii, int *radii_xy, cudaStream_t st);
+void lgs_launch_surfel_filter(int P, const float *means3D, const float *scales, float mod, const float *rotations,
+			      const float *view, int W, int H, const float *beams, int far_, int near_, int *radii, int *radii_xy,
+			      cudaStream_t st);
+void lgs_launch_surfel_mark_visible(int P, const float *means3D, const float *view, unsigned char *present, cudaStream_t st);
+void lgs_launch_surfel_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const SurfelImagePtrs &ip, uint4 *entries,
+				  const float *bg, const float *beams, float *out_color, float *out_others, int sort_all,
+				  cudaStream_t st);
+void lgs_launch_surfel_render_bwd(const FrameGeom &g, const GeomPtrs &gp, const SurfelImagePtrs &ip, const uint4 *entries,
+				  const float *bg, const float *beams, const float *dL_dpix, const float *dL_dothers, float *grad,
+				  cudaStream_t st);
+void lgs_launch_surfel_finalize_bwd(int P, const float *means3D, const float *scales, const float *rotations, const float *view,
+				    const int *radii, const float *grad, float *dL_dmean2D, float *dL_dopacity, float *dL_dcolor,
+				    float *dL_dmean3D, float *dL_dtransMat, float *dL_dscale, float *dL_drot, float *gs_depth,
+				    cudaStream_t st);

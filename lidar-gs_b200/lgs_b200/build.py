@@ -2,6 +2,7 @@
 
   lib/liblgs_b200.so                      CUDA kernels + C ABI (include/lgs_rasterizer.h), no torch dependency
   diff_lidargs_rasterization/_C*.so       torch C++ extension exporting the reference's four `_C` functions
+  diff_lidargs_surfel_rasterization/_C.so the same for the reference's surfel rasterizer (config 5)
 
 nvcc cross-compiles without a GPU.  Both artefacts are git-ignored but travel to the GPU box with gpurun.
 """
@@ -18,8 +19,9 @@ BUILD = os.path.join(PKG, "build")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "liblgs_b200.so")
 EXT = os.path.join(PKG, "diff_lidargs_rasterization", "_C.so")
-CU = ["lgs_project.cu", "lgs_bin.cu", "lgs_render_fwd.cu", "lgs_render_bwd.cu", "lgs_finalize_bwd.cu", "lgs_abi.cu"]
-HDRS = ["lgs_common.cuh", "lgs_kernels.h", os.path.join(ROOT, "include", "lgs_rasterizer.h")]
+CU = ["lgs_project.cu", "lgs_bin.cu", "lgs_render_fwd.cu", "lgs_render_bwd.cu", "lgs_finalize_bwd.cu", "lgs_abi.cu",
+      "lgs_surfel_project.cu", "lgs_surfel_render.cu"]
+HDRS = ["lgs_common.cuh", "lgs_kernels.h", "lgs_sort.cuh", "lgs_surfel.cuh", os.path.join(ROOT, "include", "lgs_rasterizer.h")]
 NVCC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -61,8 +63,15 @@ def build_lib(force=False):
     return LIB
 
 
+EXT_SURFEL = os.path.join(PKG, "diff_lidargs_surfel_rasterization", "_C.so")
+
+
 def build_ext(force=False):
-    src = os.path.join(CSRC, "ext.cpp")
+    _build_one_ext(os.path.join(CSRC, "ext_surfel.cpp"), EXT_SURFEL, "ext_surfel.log", force)
+    return _build_one_ext(os.path.join(CSRC, "ext.cpp"), EXT, "ext.log", force)
+
+
+def _build_one_ext(src, EXT, log, force=False):
     hdr = os.path.join(ROOT, "include", "lgs_rasterizer.h")
     if not (force or _newer(EXT, [src, hdr, LIB])):
         return EXT
@@ -76,7 +85,7 @@ def build_ext(force=False):
     cmd += [f"-I{p}" for p in inc] + [f"-L{p}" for p in libdirs] + [f"-L{LIBDIR}"]
     cmd += ["-llgs_b200", "-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda", "-lcudart"]
     cmd += ["-Wl,-rpath,$ORIGIN/../lib"] + [f"-Wl,-rpath,{p}" for p in libdirs]
-    _run(cmd, os.path.join(BUILD, "ext.log"))
+    _run(cmd, os.path.join(BUILD, log))
     return EXT
 
 

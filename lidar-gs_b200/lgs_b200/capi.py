@@ -14,7 +14,9 @@ _lib = None
 
 SYMBOLS = ["lgs_forward", "lgs_backward", "lgs_backward_scratch_bytes", "lgs_visible_filter", "lgs_mark_visible",
            "lgs_set_rows_per_bin", "lgs_set_sort_all", "lgs_timing_enable", "lgs_timing_collect", "lgs_last_num_instances", "lgs_launch_count",
-           "lgs_last_error", "lgs_version"]
+           "lgs_last_error", "lgs_version",
+           "lgs_surfel_forward", "lgs_surfel_backward", "lgs_surfel_backward_scratch_bytes", "lgs_surfel_visible_filter",
+           "lgs_surfel_mark_visible"]
 
 
 def load():
@@ -37,6 +39,18 @@ def load():
     L.lgs_visible_filter.argtypes = [i, i, i, i, vp, vp, fl, vp, vp, vp, vp, vp, vp, fl, fl, i, i, i, vp, vp, i, vp]
     L.lgs_mark_visible.restype = i
     L.lgs_mark_visible.argtypes = [i, vp, vp, vp, vp, vp]
+    L.lgs_surfel_forward.restype = i
+    L.lgs_surfel_forward.argtypes = [ALLOC_FN, vp, ALLOC_FN, vp, ALLOC_FN, vp, i, i, i, vp, i, i, vp, vp, vp, vp, vp, fl, vp,
+                                     vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, i, vp]
+    L.lgs_surfel_backward.restype = i
+    L.lgs_surfel_backward.argtypes = [i, i, i, i, vp, i, i, vp, vp, vp, vp, fl, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                      vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, vp]
+    L.lgs_surfel_backward_scratch_bytes.restype = C.c_size_t
+    L.lgs_surfel_backward_scratch_bytes.argtypes = [i]
+    L.lgs_surfel_visible_filter.restype = i
+    L.lgs_surfel_visible_filter.argtypes = [i, i, i, i, vp, vp, fl, vp, vp, vp, vp, vp, i, i, i, vp, vp, i, vp]
+    L.lgs_surfel_mark_visible.restype = i
+    L.lgs_surfel_mark_visible.argtypes = [i, vp, vp, vp, vp, vp]
     L.lgs_set_rows_per_bin.argtypes = [i]
     L.lgs_set_sort_all.argtypes = [i]
     L.lgs_timing_enable.argtypes = [i]
@@ -124,6 +138,74 @@ class Frame:
                             C.c_void_p(st))
         _check(rc)
         return grads
+
+
+class SurfelFrame(Frame):
+    """One forward (+ backward) of the SURFEL path through the C ABI (lgs_surfel_forward / lgs_surfel_backward)."""
+
+    def forward(self, bg, means3D, colors, opac, scales, rots, view, beams, H, W, far, near, scale_modifier=1.0,
+                stream=None, debug=False, out=None):
+        torch = self.torch
+        L = load()
+        P = means3D.shape[0]
+        if out is None:
+            out = dict(color=torch.empty((2, H, W), dtype=torch.float32, device=self.dev),
+                       others=torch.empty((7, H, W), dtype=torch.float32, device=self.dev),
+                       radii=torch.empty((P,), dtype=torch.int32, device=self.dev))
+        self.out = out
+        st = torch.cuda.current_stream(self.dev).cuda_stream if stream is None else stream
+        self.args = (bg, means3D, colors, opac, scales, rots, view, beams, H, W, far, near, scale_modifier)
+        R = L.lgs_surfel_forward(self._cbs[0], None, self._cbs[1], None, self._cbs[2], None, P, 1, 0, _ptr(bg), W, H,
+                                 _ptr(means3D), None, _ptr(colors), _ptr(opac), _ptr(scales), float(scale_modifier),
+                                 _ptr(rots), None, _ptr(view), None, None, _ptr(beams), 0, int(far), int(near),
+                                 _ptr(out["color"]), _ptr(out["others"]), None, _ptr(out["radii"]), None, int(debug),
+                                 C.c_void_p(st))
+        self.num_rendered = _check(R)
+        self.num_instances = L.lgs_last_num_instances()
+        return out
+
+    def backward(self, g_color, g_others, stream=None, debug=False, grads=None):
+        torch = self.torch
+        L = load()
+        bg, means3D, colors, opac, scales, rots, view, beams, H, W, far, near, mod = self.args
+        P = means3D.shape[0]
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=self.dev)
+        if grads is None:
+            grads = dict(means2D=f(P, 4), opacities=f(P, 1), colors=f(P, 2), means3D=f(P, 3), transMat=f(P, 9),
+                         scales=f(P, 2), rotations=f(P, 4), depth=f(P, 1),
+                         scratch=torch.empty(L.lgs_surfel_backward_scratch_bytes(P), dtype=torch.uint8, device=self.dev))
+        st = torch.cuda.current_stream(self.dev).cuda_stream if stream is None else stream
+        rc = L.lgs_surfel_backward(P, 1, 0, self.num_rendered, _ptr(bg), W, H, _ptr(means3D), None, _ptr(colors),
+                                   _ptr(scales), float(mod), _ptr(rots), None, _ptr(view), None, None, _ptr(beams),
+                                   _ptr(self.out["radii"]), _ptr(self.geom), _ptr(self.binning), _ptr(self.image),
+                                   _ptr(g_color), _ptr(g_others), _ptr(grads["scratch"]), _ptr(grads["means2D"]),
+                                   _ptr(grads["opacities"]), _ptr(grads["colors"]), _ptr(grads["means3D"]),
+                                   _ptr(grads["transMat"]), None, _ptr(grads["scales"]), _ptr(grads["rotations"]),
+                                   _ptr(grads["depth"]), int(debug), C.c_void_p(st))
+        _check(rc)
+        return grads
+
+
+def surfel_visible_filter(means3D, scales, rots, view, beams, H, W, far, near, scale_modifier=1.0, stream=None):
+    import torch
+    L = load()
+    P = means3D.shape[0]
+    radii = torch.empty((P,), dtype=torch.int32, device=means3D.device)
+    st = torch.cuda.current_stream(means3D.device).cuda_stream if stream is None else stream
+    _check(L.lgs_surfel_visible_filter(P, 0, W, H, _ptr(means3D), _ptr(scales), float(scale_modifier), _ptr(rots), None,
+                                       _ptr(view), None, _ptr(beams), 0, int(far), int(near), _ptr(radii), None, 0,
+                                       C.c_void_p(st)))
+    return radii
+
+
+def surfel_mark_visible(means3D, view, stream=None):
+    import torch
+    L = load()
+    P = means3D.shape[0]
+    out = torch.empty((P,), dtype=torch.bool, device=means3D.device)
+    st = torch.cuda.current_stream(means3D.device).cuda_stream if stream is None else stream
+    _check(L.lgs_surfel_mark_visible(P, _ptr(means3D), _ptr(view), None, _ptr(out), C.c_void_p(st)))
+    return out
 
 
 def visible_filter(means3D, scales, rots, view, beams, H, W, far, near, scale_modifier=1.0, stream=None):

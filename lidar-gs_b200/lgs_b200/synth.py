@@ -78,3 +78,30 @@ def make_config(idx, pose="identity"):
     sc = make_scene(c["P"], c["H"], c["W"], seed=1234 + idx, pose=pose)
     sc.update(make_upstream(c["H"], c["W"], seed=1234 + idx))
     return sc
+
+
+# ---- surfel path (diff_lidargs_surfel_rasterization, BASELINE config 5) -----------------------------------
+CONFIGS[5] = dict(P=5_000_000, H=128, W=2048)
+
+
+def make_surfel_scene(P, H, W, seed=1234, **kw):
+    """Same scene recipe with planar discs: scales [P, 2] (the reference's surfel rasterizer takes glm::vec2 scales)."""
+    sc = make_scene(P, H, W, seed=seed, **kw)
+    sc["scales"] = np.ascontiguousarray(sc["scales"][:, :2])
+    return sc
+
+
+def make_upstream_surfel(H, W, seed=1234):
+    """Upstream gradients of the surfel outputs: colour [2,H,W] and `others` [7,H,W]
+    (depth, alpha, normal x3, median depth, distortion: RS auxiliary.h:23-27)."""
+    rng = np.random.default_rng(seed + 104729)
+    s = 1.0 / (H * W)
+    return dict(g_color=(rng.normal(size=(2, H, W)) * s).astype(np.float32),
+                g_others=(rng.normal(size=(7, H, W)) * s).astype(np.float32))
+
+
+def make_surfel_config(idx=5, pose="identity"):
+    c = CONFIGS[idx]
+    sc = make_surfel_scene(c["P"], c["H"], c["W"], seed=1234 + idx, pose=pose)
+    sc.update(make_upstream_surfel(c["H"], c["W"], seed=1234 + idx))
+    return sc

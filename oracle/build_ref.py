@@ -26,7 +26,25 @@ OUT = os.path.join(HERE, "_ref")
 NAME = "lidargs_ref_C"
 
 
+RS = os.path.join(REF, "submodules", "diff_lidargs_surfel_rasterization")
+NAME_SURFEL = "lidargs_surfel_ref_C"
+# The surfel forward kernel prints from its inner loop for every (pixel, Gaussian) pair of rows above 31
+# (RS forward.cu:436, a hard-coded 32-beam debug check), so at H > 32 the unmodified build floods stdout and
+# cannot be timed.  The three cuda_rasterizer/*.cu files are therefore compiled with this pre-include, which
+# turns printf into a no-op AFTER <cstdio> has been seen; nothing else about the source changes.
+NOPRINTF = os.path.join(HERE, "ref_noprintf.h")
+
+
 def build(force=False):
+    return _build(R3, NAME, force, [])
+
+
+def build_surfel(force=False):
+    """oracle/_ref/lidargs_surfel_ref_C.so from submodules/diff_lidargs_surfel_rasterization (same five files)."""
+    return _build(RS, NAME_SURFEL, force, ["-include", NOPRINTF])
+
+
+def _build(R3, NAME, force, kernel_flags):
     so = os.path.join(OUT, NAME + ".so")
     if not os.path.isdir(R3):
         # GPU box / fresh clone: nothing to build from; use the prebuilt file if present
@@ -37,7 +55,7 @@ def build(force=False):
     if os.path.exists(so) and not force:
         if all(os.path.getmtime(so) > os.path.getmtime(s) for s in srcs):
             return so
-    os.makedirs(os.path.join(OUT, "obj"), exist_ok=True)
+    os.makedirs(os.path.join(OUT, "obj_" + NAME), exist_ok=True)
     from torch.utils import cpp_extension as ce
     import torch
     inc = ce.include_paths("cuda") + [sysconfig.get_paths()["include"],
@@ -48,14 +66,14 @@ def build(force=False):
     nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
     objs, cmds = [], []
     for s in srcs:
-        o = os.path.join(OUT, "obj", os.path.basename(s) + ".o")
+        o = os.path.join(OUT, "obj_" + NAME, os.path.basename(s) + ".o")
         objs.append(o)
         if s.endswith(".cu"):
             cmds.append([nvcc, "-c", s, "-o", o, "-O3", "-std=c++17",
                          "-gencode", "arch=compute_100a,code=sm_100a",
                          "-include", "cstdint", "--expt-relaxed-constexpr",
                          "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-gnu-unique",
-                         "-w"] + incf + defs)
+                         "-w"] + (kernel_flags if "cuda_rasterizer" in s else []) + incf + defs)
         else:
             cmds.append(["g++", "-c", s, "-o", o, "-O2", "-std=c++17", "-fPIC", "-w"] + incf + defs)
     with ThreadPoolExecutor(max_workers=5) as ex:
@@ -75,7 +93,11 @@ def build(force=False):
     return so
 
 
-def load():
+def load_surfel():
+    return load(NAME_SURFEL)
+
+
+def load(NAME=NAME):
     """Import the prebuilt reference extension (GPU box) -> module with the 4 `_C` functions."""
     import importlib.util
     import torch  # noqa: F401  (must be imported before the extension)
@@ -90,3 +112,4 @@ def load():
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(build_surfel(force="--force" in sys.argv))

@@ -154,3 +154,39 @@ def cov3d_numpy(scales, rots, mod=1.0):
     Sg = np.einsum("nij,nj,nkj->nik", R, s * s, R)
     return np.ascontiguousarray(np.stack([Sg[:, 0, 0], Sg[:, 0, 1], Sg[:, 0, 2], Sg[:, 1, 1], Sg[:, 1, 2], Sg[:, 2, 2]], 1),
                                 dtype=np.float32)
+
+
+# ---- surfel path ---------------------------------------------------------------------------------
+def run_surfel_abi(sc, dev="cuda:0", rows_per_bin=0, sort_all=False, backward=True):
+    """forward (+ backward) of the surfel path through the C ABI (lgs_surfel_*); numpy results + the Frame."""
+    import torch
+    from lgs_b200 import capi
+    L = capi.load()
+    L.lgs_set_rows_per_bin(int(rows_per_bin))
+    L.lgs_set_sort_all(int(bool(sort_all)))
+    d = to_torch(sc, dev)
+    fr = capi.SurfelFrame(torch.device(dev))
+    out = fr.forward(d["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"], d["viewmatrix"],
+                     d["beams"], sc["H"], sc["W"], sc["far"], sc["near"], sc.get("scale_modifier", 1.0))
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    res["num_rendered"] = fr.num_rendered
+    res["num_instances"] = fr.num_instances
+    if backward:
+        gr = fr.backward(d["g_color"], d["g_others"])
+        torch.cuda.synchronize()
+        res["grads"] = {k: v.cpu().numpy() for k, v in gr.items() if v is not None and k != "scratch"}
+    L.lgs_set_rows_per_bin(0)
+    L.lgs_set_sort_all(0)
+    return res, fr
+
+
+def surfel_oracle_run(sc, backward=True):
+    """The checker: CPU restatement of the reference surfel rasterizer (oracle/lgs_oracle_surfel.c)."""
+    import lgs_oracle_surfel as S
+    f = S.Forward(sc)
+    out = dict(color=f.color, others=f.others, radii=f.radii, num_rendered=f.num_rendered)
+    if backward:
+        out["grads"] = f.backward(sc["g_color"], sc["g_others"])
+    out["internals"] = f.internals()
+    f.close()
+    return out
