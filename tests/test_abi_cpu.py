@@ -147,3 +147,75 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "lgs_oracle" not in text and "oracle/" not in text.replace("oracle/make_goldens", ""), f
+
+
+# ---- surfel path (diff_lidargs_surfel_rasterization) ------------------------------------------------------------
+SURFEL_SETTINGS_FIELDS = (  # RS/__init__.py:179-193
+    "image_height", "image_width", "bg", "scale_modifier", "depth_threshold", "viewmatrix", "projmatrix", "sh_degree",
+    "campos", "prefiltered", "beam_inclinations", "lidar_far", "lidar_near", "debug")
+
+
+def test_header_declares_the_surfel_entry_points():
+    names = _declared_functions()
+    for n in ("lgs_surfel_forward", "lgs_surfel_backward", "lgs_surfel_backward_scratch_bytes", "lgs_surfel_visible_filter",
+              "lgs_surfel_mark_visible"):
+        assert n in names
+
+
+def test_surfel_host_side_validation_without_device():
+    from lgs_b200 import capi
+    L = capi.load()
+    assert L.lgs_surfel_backward_scratch_bytes(1000) >= 1000 * 20 * 4
+    assert L.lgs_surfel_backward_scratch_bytes(1000) % 256 == 0
+    assert L.lgs_surfel_mark_visible(-1, None, None, None, None, None) == -1
+    assert L.lgs_surfel_mark_visible(5, None, None, None, None, None) == -1 and b"null input" in L.lgs_last_error()
+    assert L.lgs_surfel_visible_filter(-3, 0, 64, 64, None, None, 1.0, None, None, None, None, None, 0, 80, 0, None, None, 0,
+                                       None) == -1
+    assert L.lgs_surfel_visible_filter(0, 0, 64, 64, None, None, 1.0, None, None, None, None, None, 0, 80, 0, None, None, 0,
+                                       None) == 0
+    assert L.lgs_surfel_backward(0, 0, 0, 0, None, 64, 64, None, None, None, None, 1.0, None, None, None, None, None, None,
+                                 None, None, None, None, None, None, None, None, None, None, None, None, None, None, None,
+                                 None, 0, None) == 0
+    assert L.lgs_surfel_backward(4, 0, 0, 0, None, 64, 64, None, None, None, None, 1.0, None, None, None, None, None, None,
+                                 None, None, None, None, None, None, None, None, None, None, None, None, None, None, None,
+                                 None, 0, None) == -1
+
+
+def test_surfel_dropin_package_surface():
+    import inspect
+
+    import torch
+
+    import diff_lidargs_surfel_rasterization as dlr
+    assert dlr.GaussianRasterizationSettings._fields == SURFEL_SETTINGS_FIELDS
+    for fn in ("rasterize_gaussians", "rasterize_gaussians_backward", "rasterize_aussians_filter", "mark_visible"):
+        assert hasattr(dlr._C, fn)  # RS ext.cpp:15-19
+    sig = inspect.signature(dlr.GaussianRasterizer.forward)
+    assert list(sig.parameters) == ["self", "means3D", "means2D", "opacities", "shs", "colors_precomp", "scales",
+                                    "rotations", "cov3D_precomp"]
+    assert list(inspect.signature(dlr.GaussianRasterizer.visible_filter).parameters) == [
+        "self", "means3D", "scales", "rotations", "cov3D_precomp"]
+    rs = dlr.GaussianRasterizationSettings(*([None] * 14))
+    rast = dlr.GaussianRasterizer(rs)
+    assert isinstance(rast, torch.nn.Module) and rast.raster_settings is rs
+    z = torch.zeros(4, 3)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        rast(z, z, z[:, :1])
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        rast(z, z, z[:, :1], colors_precomp=z[:, :2])
+
+
+def test_surfel_extension_rejects_cpu_tensors_instead_of_falling_back():
+    import torch
+
+    import diff_lidargs_surfel_rasterization as dlr
+    e = torch.Tensor([])
+    z = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dlr._C.rasterize_aussians_filter(z, z[:, :2], torch.zeros(4, 4), 1.0, e, torch.eye(4), torch.eye(4), torch.zeros(8),
+                                         8, 64, False, 80, 0, False)
+    with pytest.raises(RuntimeError, match="num_points, 3"):
+        dlr._C.rasterize_aussians_filter(torch.zeros(4, 2), z[:, :2], torch.zeros(4, 4), 1.0, e, torch.eye(4), torch.eye(4),
+                                         torch.zeros(8), 8, 64, False, 80, 0, False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dlr._C.mark_visible(z, torch.eye(4), torch.eye(4))
