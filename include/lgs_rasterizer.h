@@ -167,6 +167,24 @@ int lgs_surfel_visible_filter(int P, int M, int width, int height,
 int lgs_surfel_mark_visible(int P, const float *means3D, const float *viewmatrix,
                             const float *projmatrix, unsigned char *present, void *stream);
 
+/* ==== frame-parallel gradient exchange (no reference counterpart: the reference is single-GPU) ============
+ * A frame's backward leaves most Gaussians untouched (zero gradient), so instead of a dense all-reduce of the
+ * 13 P-float gradient bucket the ranks can all-gather only their touched rows (lgs_b200/dp.py SparseExchange):
+ *   lgs_backward_touched : device pointers to the id list / count lgs_backward() left in its scratch
+ *   lgs_grad_pack        : (cap + 1) rows of 64 bytes: row 0 = {count, cap}, row i + 1 = {id, dmean3D 3, dscale 3,
+ *                          dopacity, drot 4, dcolor 2, pad 2} of the i-th touched Gaussian
+ *   lgs_grad_scatter_add : adds the rows of every OTHER rank (gathered = nranks packed buffers back to back) into
+ *                          the local dense gradient arrays -> the same sums a dense all-reduce gives
+ */
+int lgs_backward_touched(float *grad_scratch, int P, const uint32_t **ids, const uint32_t **count);
+size_t lgs_grad_pack_bytes(int cap);
+int lgs_grad_pack(const uint32_t *ids, const uint32_t *count, int cap,
+                  const float *dL_dmean3D, const float *dL_dscale, const float *dL_drot,
+                  const float *dL_dopacity, const float *dL_dcolor, float *packed, void *stream);
+int lgs_grad_scatter_add(int P, const float *gathered, int nranks, int my_rank, int cap,
+                         float *dL_dmean3D, float *dL_dscale, float *dL_drot,
+                         float *dL_dopacity, float *dL_dcolor, void *stream);
+
 /* ---- knobs and introspection (no reference counterpart) -------------------------------- */
 
 /* Rows of 16x1 tiles that share one depth-binned list (1, 2, 4, 8 or 16; 0 = auto). */

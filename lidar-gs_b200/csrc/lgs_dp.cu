@@ -1,0 +1,100 @@
+// lgs_dp.cu -- frame-parallel gradient exchange without the zeros.
+//
+// The reference is single-GPU; the frame-parallel step of this repo (lgs_b200/dp.py, bench.py --gpus N) sums the
+// parameter gradients of the ranks' frames.  A frame's backward only touches the Gaussians in the list prefixes its rays
+// consumed -- on BASELINE config 3 about 33 k of 2 M -- so a dense all-reduce of the 13 P-float bucket moves 104 MB of
+// which 98 % is zeros.  These two kernels turn the collective into an all-gather of the touched rows:
+//   pack        : (id, 13 gradient floats) of every touched Gaussian -> one 64-byte row; row 0 is a header with the count
+//   scatter_add : rows gathered from the OTHER ranks are added into the local dense gradient arrays
+// after which every rank holds the same sums a dense all-reduce would have produced.
+#include "../../include/lgs_rasterizer.h"
+#include "lgs_common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+grad_pack_kernel(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ count, int cap, const float *__restrict__ d_means3D,
+		 const float *__restrict__ d_scales, const float *__restrict__ d_rot, const float *__restrict__ d_opac,
+		 const float *__restrict__ d_colors, float4 *__restrict__ packed)
+{
+	const unsigned n = min(*count, (unsigned)cap);
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+		packed[0] = make_float4(__uint_as_float(*count), __uint_as_float((unsigned)cap), 0.f, 0.f);
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const unsigned id = ids[i];
+		const float *m = d_means3D + 3 * (size_t)id, *s = d_scales + 3 * (size_t)id, *c = d_colors + 2 * (size_t)id;
+		const float4 r = *reinterpret_cast<const float4 *>(d_rot + 4 * (size_t)id);
+		float4 *row = packed + 4 * ((size_t)i + 1);
+		row[0] = make_float4(__uint_as_float(id), m[0], m[1], m[2]);
+		row[1] = make_float4(s[0], s[1], s[2], d_opac[id]);
+		row[2] = r;
+		row[3] = make_float4(c[0], c[1], 0.f, 0.f);
+	}
+}
+
+__global__ void __launch_bounds__(256)
+grad_scatter_add_kernel(int P, const float4 *__restrict__ all, int nranks, int my_rank, int cap, float *__restrict__ d_means3D,
+			float *__restrict__ d_scales, float *__restrict__ d_rot, float *__restrict__ d_opac, float *__restrict__ d_colors)
+{
+	const size_t stride = 4 * ((size_t)cap + 1);
+	for (int r = 0; r < nranks; r++) {
+		if (r == my_rank) continue;
+		const float4 *buf = all + (size_t)r * stride;
+		const unsigned n = min(__float_as_uint(buf[0].x), (unsigned)cap);
+		for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+			const float4 *row = buf + 4 * ((size_t)i + 1);
+			const float4 a = row[0], b = row[1], c = row[2], d = row[3];
+			const unsigned id = __float_as_uint(a.x);
+			if (id >= (unsigned)P) continue;
+			// several ranks may touch the same Gaussian: atomics (rows of ONE rank are unique, so contention is at most nranks - 1)
+			atomicAdd(d_means3D + 3 * (size_t)id, a.y); atomicAdd(d_means3D + 3 * (size_t)id + 1, a.z); atomicAdd(d_means3D + 3 * (size_t)id + 2, a.w);
+			atomicAdd(d_scales + 3 * (size_t)id, b.x); atomicAdd(d_scales + 3 * (size_t)id + 1, b.y); atomicAdd(d_scales + 3 * (size_t)id + 2, b.z);
+			atomicAdd(d_opac + id, b.w);
+			atomicAdd(d_rot + 4 * (size_t)id, c.x); atomicAdd(d_rot + 4 * (size_t)id + 1, c.y);
+			atomicAdd(d_rot + 4 * (size_t)id + 2, c.z); atomicAdd(d_rot + 4 * (size_t)id + 3, c.w);
+			atomicAdd(d_colors + 2 * (size_t)id, d.x); atomicAdd(d_colors + 2 * (size_t)id + 1, d.y);
+		}
+	}
+}
+
+} // namespace
+
+extern "C" {
+
+int lgs_backward_touched(float *grad_scratch, int P, const uint32_t **ids, const uint32_t **count)
+{
+	if (!grad_scratch || P <= 0 || !ids || !count) return LGS_EINVAL;
+	// layout of the backward scratch (lgs_abi.cu): [P, 20] rows | touched bitmask + count | list of touched ids
+	char *p = (char *)grad_scratch + lgs_al((size_t)P * LGS_GRAD_STRIDE * sizeof(float));
+	const uint32_t *touched = (const uint32_t *)p;
+	*count = touched + ((size_t)P + 31) / 32;
+	*ids = (const uint32_t *)(p + lgs_al((((size_t)P + 31) / 32) * 4 + 16));
+	return 0;
+}
+
+size_t lgs_grad_pack_bytes(int cap) { return ((size_t)(cap > 0 ? cap : 0) + 1) * 64; }
+
+int lgs_grad_pack(const uint32_t *ids, const uint32_t *count, int cap, const float *dL_dmean3D, const float *dL_dscale,
+		  const float *dL_drot, const float *dL_dopacity, const float *dL_dcolor, float *packed, void *stream)
+{
+	if (!ids || !count || cap < 0 || !dL_dmean3D || !dL_dscale || !dL_drot || !dL_dopacity || !dL_dcolor || !packed) return LGS_EINVAL;
+	const int blocks = max(1, min((cap + 255) / 256, 148 * 4));
+	grad_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ids, count, cap, dL_dmean3D, dL_dscale, dL_drot, dL_dopacity, dL_dcolor,
+								    (float4 *)packed);
+	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;
+}
+
+int lgs_grad_scatter_add(int P, const float *gathered, int nranks, int my_rank, int cap, float *dL_dmean3D, float *dL_dscale,
+			 float *dL_drot, float *dL_dopacity, float *dL_dcolor, void *stream)
+{
+	if (P <= 0 || !gathered || nranks < 1 || my_rank < 0 || my_rank >= nranks || cap < 0 || !dL_dmean3D || !dL_dscale || !dL_drot ||
+	    !dL_dopacity || !dL_dcolor)
+		return LGS_EINVAL;
+	if (nranks == 1) return 0;
+	const int blocks = max(1, min((cap + 255) / 256, 148 * 4));
+	grad_scatter_add_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P, (const float4 *)gathered, nranks, my_rank, cap, dL_dmean3D,
+									   dL_dscale, dL_drot, dL_dopacity, dL_dcolor);
+	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;
+}
+
+} // extern "C"

@@ -324,14 +324,20 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 							const float4 uu = st.u[jj];
 							const unsigned rays = lgs_smem_addr(sray + epg * 32 + 16 * eh), tcs = lgs_smem_addr(tcol);
 							float amax = 0.f;
-							while (lv) {
-								const int p = __ffs(lv) - 1;
+							while (lv) { // two live pixels per trip: two independent dependency chains per lane
+								const int p0 = __ffs(lv) - 1;
 								lv &= lv - 1;
-								const float4 rr = lgs_lds128(rays + 16u * p);
-								float alpha = 0.f;
-								if (rowok) alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, q0, q1, q2, q3, uu);
-								lgs_sts32(tcs + (unsigned)(4 * LD) * p, alpha);
-								amax = fmaxf(amax, alpha);
+								const int p1 = lv ? __ffs(lv) - 1 : p0; // odd count: the last pixel is evaluated twice (same value, same slot)
+								lv &= lv - 1;
+								const float4 r0 = lgs_lds128(rays + 16u * p0), r1 = lgs_lds128(rays + 16u * p1);
+								float a0 = 0.f, a1 = 0.f;
+								if (rowok) {
+									a0 = lgs_pair_alpha(r0.x, r0.y, r0.z, q0, q1, q2, q3, uu);
+									a1 = lgs_pair_alpha(r1.x, r1.y, r1.z, q0, q1, q2, q3, uu);
+								}
+								lgs_sts32(tcs + (unsigned)(4 * LD) * p0, a0);
+								lgs_sts32(tcs + (unsigned)(4 * LD) * p1, a1);
+								amax = fmaxf(amax, fmaxf(a0, a1));
 							}
 							m32 = __ballot_sync(0xffffffffu, amax != 0.f);
 						} else {

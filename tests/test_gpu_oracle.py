@@ -158,3 +158,56 @@ def test_visible_filter_matches_oracle_on_anchor_like_input():
     assert ((r > 0) != (ro > 0)).sum() == 0
     m = capi.mark_visible(d["means3D"], d["viewmatrix"]).cpu().numpy()
     assert np.array_equal(m, O.mark_visible(sc["means3D"], sc["viewmatrix"]))
+
+
+def test_sparse_gradient_exchange_equals_dense_sum():
+    """csrc/lgs_dp.cu on ONE device: two "ranks" render two poses; packing each rank's touched rows, concatenating them
+    the way all_gather_into_tensor would and scatter-adding the other rank's rows must give the dense sum of the two
+    gradient buckets (what the all-reduce computes).  The NCCL leg itself is exercised by bench.py --gpus N, which
+    asserts the same equality before timing."""
+    import torch
+    from lgs_b200 import capi, dp, synth
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(P=30000, H=16, W=256, seed=77, pose="random")
+    sc.update(synth.make_upstream(16, 256, seed=77))
+    P = sc["P"]
+    d = util.to_torch(sc, dev)
+    buckets, packs, caps = [], [], []
+    xs = dp.SparseExchange(P, dev)
+    views_of = lambda b: {n: b.views[n] for n in ("means3D", "scales", "rotations", "opacities", "colors")}
+    for r in range(2):
+        view = d["viewmatrix"].clone()
+        view[3, 0] += 0.7 * r  # second "rank": the sensor shifted along x
+        fr = capi.Frame(dev)
+        fr.forward(d["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"], view, d["beams"], 16, 256, 80, 0)
+        b = dp.GradBucket(P, dev)
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        grads = dict(views_of(b), means2D=f(P, 4), cov3D=None,
+                     scratch=torch.empty(capi.load().lgs_backward_scratch_bytes(P), dtype=torch.uint8, device=dev))
+        fr.backward(d["g_color"], d["g_depth"], d["g_occ"], grads=grads)
+        ids_ptr, cnt_ptr = xs.touched(grads["scratch"])
+        cnt = int(dp._device_u32(cnt_ptr, dev).item())
+        assert 0 < cnt < P
+        # every Gaussian with a non-zero gradient is in the list
+        ids = torch.as_tensor(type("A", (), {"__cuda_array_interface__": dict(shape=(cnt,), typestr="<i4", data=(int(ids_ptr), False), version=3)})(), device=dev).long()
+        nz = (b.flat.view(-1) != 0)
+        nz_g = torch.zeros(P, dtype=torch.bool, device=dev)
+        for name, v in views_of(b).items():
+            nz_g |= (v != 0).any(dim=1)
+        listed = torch.zeros(P, dtype=torch.bool, device=dev)
+        listed[ids] = True
+        assert bool((listed | ~nz_g).all()) and ids.unique().numel() == cnt
+        buckets.append((b, grads))
+        caps.append(cnt)
+    cap = (max(caps) + 1023) // 1024 * 1024
+    for (b, grads) in buckets:
+        ids_ptr, cnt_ptr = xs.touched(grads["scratch"])
+        packs.append(xs.pack(ids_ptr, cnt_ptr, cap, views_of(b)).clone())
+    gathered = torch.cat(packs)
+    want = buckets[0][0].flat + buckets[1][0].flat
+    for r in range(2):
+        got = dp.GradBucket(P, dev)
+        got.flat.copy_(buckets[r][0].flat)
+        xs.scatter_add(gathered, 2, r, cap, views_of(got))
+        torch.cuda.synchronize()
+        assert torch.equal(got.flat, want) or float((got.flat - want).abs().max()) <= 1e-7 * float(want.abs().max())
