@@ -24,6 +24,8 @@
 
 namespace {
 
+#define LGS_HEAVY_BATCHES 24 // batches after which a still-live bin is treated as heavy (see "Straggler mode" below)
+
 template <int RB> struct FwdCfg {
 	static constexpr int NPG = RB >= 2 ? RB / 2 : 1;     // 32-pixel groups (2 rows x 16 columns)
 	static constexpr int NEV = 2 * NPG;                   // evaluate warps: one per (pixel group, row)
@@ -44,8 +46,9 @@ template <int RB> struct FwdCfg {
 	static constexpr size_t O_LIVE = O_MASK + 4 * 2 * NPG * 2;            // [2][group]: pixels not yet terminated
 	static constexpr size_t O_LOC = O_LIVE + 4 * 2 * NPG;
 	static constexpr size_t O_TAIL = (O_LOC + 4 * (LGS_NB + 1) + 15) / 16 * 16; // straggler state: TL x (float4 + uint4)
-	static constexpr int TL = 2 * NW;                     // switch to straggler mode when <= TL pixels of the bin are live
-	static constexpr size_t O_FLAG = O_TAIL + 32 * TL;    // one byte per entry of the chunk: bit (2 * group + row) = "blended in that row"
+	static constexpr int TL = 2 * NW;                     // switch to straggler mode when <= TL pixels of the bin are live ...
+	static constexpr int TLCAP = 32 * NPG;                // ... or, whatever the count, once the bin has proven heavy (LGS_HEAVY_BATCHES)
+	static constexpr size_t O_FLAG = O_TAIL + 32 * TLCAP;    // one byte per entry of the chunk: bit (2 * group + row) = "blended in that row"
 	static constexpr size_t BYTES = O_FLAG + LGS_SEG_CAP;
 	// straggler mode stages whole sub-chunks of TSUB entries (100 B each) in the memory of the two alpha tiles
 	static constexpr int TSUB_ = (int)(2 * TILE / 100) / 32 * 32;
@@ -133,7 +136,7 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 	const int erow = rg * RB + 2 * epg + eh;
 	// straggler mode (see below): per-slot pixel state lives in shared memory between segments
 	float4 *ts0 = reinterpret_cast<float4 *>(smem + C::O_TAIL);        // T, C0, C1, D
-	uint4 *ts1 = reinterpret_cast<uint4 *>(smem + C::O_TAIL) + C::TL;  // last, stop, pixel (group * 32 + lane), done
+	uint4 *ts1 = reinterpret_cast<uint4 *>(smem + C::O_TAIL) + C::TLCAP;  // last, stop, pixel (group * 32 + lane), done
 	unsigned *sflagw = reinterpret_cast<unsigned *>(smem + C::O_FLAG);
 	bool tail = false;
 	int ntail = 0, myslot = -1;
@@ -196,7 +199,9 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 				int nlive = 0;
 #pragma unroll
 				for (int i = 0; i < NPG; i++) nlive += __popc(slive[((gb + 1) & 1) * NPG + i]);
-				if (nlive <= C::TL) {
+				// A bin whose rays are still alive after LGS_HEAVY_BATCHES batches never saturates (sky, image border): it is on the
+				// frame's critical path, and the barrier-per-batch pipeline runs it at a fraction of the SM's issue rate.
+				if (nlive <= C::TL || gb >= LGS_HEAVY_BATCHES) {
 					tail = true;
 					ntail = nlive;
 					if (blender) {
@@ -240,36 +245,46 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 						const int prow = rg * RB + 2 * (int)(s1.z >> 5) + (int)((s1.z >> 4) & 1u);
 						const unsigned posb = s0 + c0 + (unsigned)sub0;
 						bool fin_ = false;
-						for (int g0 = 0; g0 < sm && !fin_; g0 += 32) {
-							const int j = g0 + lane;
-							const bool valid = j < sm;
-							const int jj = valid ? j : 0;
-							const unsigned yp = typ[jj];
-							float alpha = 0.f;
-							if (valid && prow >= (int)(yp & 0xffffu) && prow < (int)(yp >> 16))
-								alpha = lgs_pair_alpha(rr.x, rr.y, rr.z, tq[jj], tq[C::TSUB + jj], tq[2 * C::TSUB + jj],
-										       tq[3 * C::TSUB + jj], tu[jj]);
-							unsigned msk = __ballot_sync(0xffffffffu, alpha != 0.f);
-							while (msk) {
-								const int b = __ffs(msk) - 1;
-								msk &= msk - 1;
-								const float al = __shfl_sync(0xffffffffu, alpha, b);
-								const float4 f = tfeat[g0 + b];
-								const float test_T = __fmul_rn(s0v.x, __fsub_rn(1.0f, al));
-								if (test_T < 0.0001f) {
-									fin_ = true;
-									s1.y = posb + g0 + b + 1;
-									s1.w = 1u;
-									break;
-								}
-								s0v.y = __fmaf_rn(s0v.x, __fmul_rn(al, f.x), s0v.y);
-								s0v.z = __fmaf_rn(s0v.x, __fmul_rn(al, f.y), s0v.z);
-								s0v.w = __fmaf_rn(s0v.x, __fmul_rn(al, f.z), s0v.w);
-								s0v.x = test_T;
-								s1.x = posb + g0 + b + 1;
-								if (RB <= 8 && lane == 0) {
-									const int je = sub0 + g0 + b;
-									atomicOr(&sflagw[je >> 2], (1u << (2 * (s1.z >> 5) + ((s1.z >> 4) & 1u))) << (8 * (je & 3)));
+						for (int g0 = 0; g0 < sm && !fin_; g0 += 64) {
+							// two groups of 32 entries per trip: their alphas are two independent dependency chains; the blend
+							// then consumes group A, then group B (evaluating B early never changes a result)
+							float alpha2[2];
+#pragma unroll
+							for (int h = 0; h < 2; h++) {
+								const int j = g0 + 32 * h + lane;
+								const bool valid = j < sm;
+								const int jj = valid ? j : 0;
+								const unsigned yp = typ[jj];
+								alpha2[h] = 0.f;
+								if (valid && prow >= (int)(yp & 0xffffu) && prow < (int)(yp >> 16))
+									alpha2[h] = lgs_pair_alpha(rr.x, rr.y, rr.z, tq[jj], tq[C::TSUB + jj], tq[2 * C::TSUB + jj],
+												   tq[3 * C::TSUB + jj], tu[jj]);
+							}
+#pragma unroll
+							for (int h = 0; h < 2; h++) {
+								const int gh = g0 + 32 * h;
+								unsigned msk = __ballot_sync(0xffffffffu, alpha2[h] != 0.f);
+								while (msk && !fin_) {
+									const int b = __ffs(msk) - 1;
+									msk &= msk - 1;
+									const float al = __shfl_sync(0xffffffffu, alpha2[h], b);
+									const float4 f = tfeat[gh + b];
+									const float test_T = __fmul_rn(s0v.x, __fsub_rn(1.0f, al));
+									if (test_T < 0.0001f) {
+										fin_ = true;
+										s1.y = posb + gh + b + 1;
+										s1.w = 1u;
+										break;
+									}
+									s0v.y = __fmaf_rn(s0v.x, __fmul_rn(al, f.x), s0v.y);
+									s0v.z = __fmaf_rn(s0v.x, __fmul_rn(al, f.y), s0v.z);
+									s0v.w = __fmaf_rn(s0v.x, __fmul_rn(al, f.z), s0v.w);
+									s0v.x = test_T;
+									s1.x = posb + gh + b + 1;
+									if (RB <= 8 && lane == 0) {
+										const int je = sub0 + gh + b;
+										atomicOr(&sflagw[je >> 2], (1u << (2 * (s1.z >> 5) + ((s1.z >> 4) & 1u))) << (8 * (je & 3)));
+									}
 								}
 							}
 						}
@@ -426,7 +441,7 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 	}
 	if (tid == 0) {
 		sorted_end[bin] = (k < LGS_NB) ? sloc[k] : ntotal;
-		cta_prof[bin] = make_uint4(t0us, (unsigned)(clock64() - clk0), lgs_smid(), gb | (tail ? 0x80000000u : 0u) | ((unsigned)ntail << 24));
+		cta_prof[bin] = make_uint4(t0us, (unsigned)(clock64() - clk0), lgs_smid(), gb | (tail ? 0x80000000u : 0u) | ((unsigned)min(ntail, 127) << 24));
 	}
 	if (inside) {
 		const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
