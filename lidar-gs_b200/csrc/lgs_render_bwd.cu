@@ -22,6 +22,8 @@ namespace {
 
 #define BWD_BATCH 64                  // entries per batch of the backward replay
 #define BWD_LD (BWD_BATCH + 4)        // tile row stride, see LGS_TILE_LD
+#define BWD_CHUNK 512                 // list entries scanned per chunk: only those forward flagged as blended into this
+                                      // pixel group's rows survive (order preserved) and are staged at all
 
 // One CTA per (bin, 32-pixel group): the lists are read-only here, so the groups of a bin need not share a CTA, and
 // a bin whose rays never terminate (thousands of replayed entries) is spread over RB/2 CTAs instead of serialising.
@@ -32,9 +34,10 @@ struct BwdCfg {
 	static constexpr int NW = NTASK < 16 ? NTASK : 16;
 	static constexpr int NT = NW * 32;
 	static constexpr size_t TILE = 4 * (size_t)NPG * 32 * BWD_LD;    // [group][pixel][BWD_LD]
-	static constexpr int STAGE = 6 * 16 * BWD_BATCH + 12 * BWD_BATCH;     // 4 record quarters, feat, u, yp, id, row flags
+	static constexpr int STAGE = 6 * 16 * BWD_BATCH + 16 * BWD_BATCH;     // 4 record quarters, feat, u, yp, id, row flags, list position
 	static constexpr size_t O_STAGE = 0;                                  // 2 staging buffers (double buffered)
-	static constexpr size_t O_RAY = O_STAGE + 2 * STAGE;                  // float4 ray per pixel
+	static constexpr size_t O_Q = O_STAGE + 2 * STAGE;                    // uint4 [BWD_CHUNK]: surviving entries (id, y0 | y1 << 16, list position, flags)
+	static constexpr size_t O_RAY = O_Q + 16 * BWD_CHUNK;                 // float4 ray per pixel
 	static constexpr size_t O_G = O_RAY + 16 * 32 * NPG;                  // float4 (g_color0, g_color1, g_depth, -) per pixel
 	static constexpr size_t O_TA = O_G + 16 * 32 * NPG;
 	static constexpr size_t O_TB = O_TA + TILE;
@@ -42,7 +45,8 @@ struct BwdCfg {
 	static constexpr size_t O_MASK = O_LAST + 4 * 32 * NPG;
 	static constexpr size_t O_LIVE = O_MASK + 4 * NPG * NEG * 2;
 	static constexpr size_t O_MAX = O_LIVE + 2 * 4 * NPG;                // slive is double buffered by batch parity
-	static constexpr size_t BYTES = O_MAX + 16;
+	static constexpr size_t O_WCNT = O_MAX + 16;
+	static constexpr size_t BYTES = O_WCNT + 4 * 16;
 };
 
 struct BStage {
@@ -52,6 +56,7 @@ struct BStage {
 	unsigned *yp;  // y0 | y1 << 16
 	unsigned *id;  // Gaussian index
 	unsigned *flag; // bit (2 * group + row): forward blended this entry into a pixel of that row
+	unsigned *pos;  // position of the entry in the bin's list
 	__device__ __forceinline__ BStage(unsigned char *base)
 	{
 		q = reinterpret_cast<float4 *>(base);
@@ -60,6 +65,7 @@ struct BStage {
 		yp = reinterpret_cast<unsigned *>(u + BWD_BATCH);
 		id = yp + BWD_BATCH;
 		flag = id + BWD_BATCH;
+		pos = flag + BWD_BATCH;
 	}
 };
 
@@ -68,10 +74,10 @@ __device__ __forceinline__ void bstage_batch(const BStage &st, const float4 *__r
 {
 	for (int i = t; i < 4 * bn; i += nthreads) {
 		const int j = i >> 2, part = i & 3;
-		const uint4 e = ent[j];
-		const float4 q = rec[4 * (size_t)e.y + part];
+		const uint4 e = ent[j]; // survivor queue entry: (id, y0 | y1 << 16, list position, flags)
+		const float4 q = rec[4 * (size_t)e.x + part];
 		st.q[part * BWD_BATCH + j] = q;
-		if (part == 0) { st.yp[j] = e.z; st.id[j] = e.y; st.flag[j] = e.w; }
+		if (part == 0) { st.yp[j] = e.y; st.id[j] = e.x; st.flag[j] = e.w; st.pos[j] = e.z; }
 		else if (part == 1) st.feat[j].z = q.w;
 		else {
 			const float uu = lgs_dot_self(q.x, q.y, q.z), r = lgs_div_prep(uu);
@@ -148,12 +154,53 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 	const unsigned maxc = smax[0]; // deepest contributor of the bin: nothing behind it is replayed
 	if (maxc == 0) return;
 
-	bstage_batch(BStage(smem + C::O_STAGE), rec, entries + base, (int)min((unsigned)B, maxc), tid, NT);
+	uint4 *sq = reinterpret_cast<uint4 *>(smem + C::O_Q);
+	unsigned *swcnt = reinterpret_cast<unsigned *>(smem + C::O_WCNT);
+	const unsigned rowbits = 3u << (2 * pgc); // forward's blended-row flags of this group's two rows
+	const uint4 *ent = entries + base;
+	for (unsigned clo = 0; clo < maxc; clo += BWD_CHUNK) {
+	// ---- 0: scan BWD_CHUNK list entries; keep, in order, those forward blended into one of this group's rows ----
+	const unsigned nchunk = min((unsigned)BWD_CHUNK, maxc - clo);
+	uint4 ev[BWD_CHUNK / NT];
+	unsigned keepm = 0, mycount = 0;
+#pragma unroll
+	for (int r = 0; r < BWD_CHUNK / NT; r++) { // warp w owns the contiguous span [w * BWD_CHUNK / NW, (w + 1) * BWD_CHUNK / NW)
+		const unsigned i = (unsigned)warp * (BWD_CHUNK / NW) + (unsigned)r * 32 + lane;
+		ev[r] = make_uint4(0, 0, 0, 0);
+		if (i < nchunk) ev[r] = ent[clo + i];
+		const bool keep = (ev[r].w & rowbits) != 0;
+		const unsigned mk = __ballot_sync(0xffffffffu, keep);
+		if (keep) keepm |= 1u << r;
+		mycount += __popc(mk);
+	}
+	if (lane == 0) swcnt[warp] = mycount;
+	__syncthreads(); // (also: the previous chunk's gradient phase is done with the queue, the staging buffers and the tiles)
+	unsigned woff = 0, nq = 0;
+#pragma unroll
+	for (int w = 0; w < NW; w++) {
+		const unsigned c = swcnt[w];
+		if (w < warp) woff += c;
+		nq += c;
+	}
+#pragma unroll
+	for (int r = 0; r < BWD_CHUNK / NT; r++) {
+		const bool keep = (keepm >> r) & 1u;
+		const unsigned mk = __ballot_sync(0xffffffffu, keep);
+		if (keep) {
+			const unsigned i = (unsigned)warp * (BWD_CHUNK / NW) + (unsigned)r * 32 + lane;
+			sq[woff + __popc(mk & ((1u << lane) - 1u))] = make_uint4(ev[r].y, ev[r].z, clo + i, ev[r].w);
+		}
+		woff += __popc(mk);
+	}
+	__syncthreads();
+	if (nq == 0) continue;
+
+	bstage_batch(BStage(smem + C::O_STAGE), rec, sq, (int)min((unsigned)B, nq), tid, NT);
 	int ib = 0;
-	for (unsigned lo = 0; lo < maxc; lo += B, ib++) {
-		const int bn = (int)min((unsigned)B, maxc - lo);
+	for (unsigned lo = 0; lo < nq; lo += B, ib++) {
+		const int bn = (int)min((unsigned)B, nq - lo);
 		const BStage st(smem + C::O_STAGE + (ib & 1) * C::STAGE);
-		const bool lane_live = lastc > lo;
+		const bool lane_live = lastc > sq[lo].z; // the pixel still has contributors at or behind this batch
 		unsigned *live = slive + (ib & 1) * NPG; // other parity: warps still in the previous batch's gradient phase read theirs
 		if (blender) {
 			const unsigned lv = __ballot_sync(0xffffffffu, lane_live);
@@ -188,7 +235,7 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			const float4 uu = st.u[jj];
 			float *tcol = tileA + (size_t)(pg * 32 + 16 * h) * LD + j;
 			const unsigned rays = lgs_smem_addr(sray + pg * 32 + 16 * h), tcs = lgs_smem_addr(tcol);
-			const unsigned pos = lo + (unsigned)j;
+			const unsigned pos = st.pos[jj];
 			float amax = 0.f;
 			while (lv) { // two live pixels per trip: two independent dependency chains per lane
 				const int p0 = __ffs(lv) - 1;
@@ -247,13 +294,13 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 					}
 				}
 			}
-			if (!OVERLAP && lo + B < maxc) {
-				bstage_batch(BStage(smem + C::O_STAGE + ((ib + 1) & 1) * C::STAGE), rec, entries + base + lo + B,
-					     (int)min((unsigned)B, maxc - lo - B), tid, NT);
+			if (!OVERLAP && lo + B < nq) {
+				bstage_batch(BStage(smem + C::O_STAGE + ((ib + 1) & 1) * C::STAGE), rec, sq + lo + B,
+					     (int)min((unsigned)B, nq - lo - B), tid, NT);
 			}
-		} else if (lo + B < maxc) {
-			bstage_batch(BStage(smem + C::O_STAGE + ((ib + 1) & 1) * C::STAGE), rec, entries + base + lo + B,
-				     (int)min((unsigned)B, maxc - lo - B), tid - NPG * 32, NT - NPG * 32);
+		} else if (lo + B < nq) {
+			bstage_batch(BStage(smem + C::O_STAGE + ((ib + 1) & 1) * C::STAGE), rec, sq + lo + B,
+				     (int)min((unsigned)B, nq - lo - B), tid - NPG * 32, NT - NPG * 32);
 		}
 		__syncthreads();
 
@@ -308,6 +355,7 @@ render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			red_add_v4(row + 16, i22 * (uu.y * aYx - 2.f * d.x * aYu), i22 * (uu.y * aYy - 2.f * d.y * aYu),
 				   i22 * (uu.y * aYz - 2.f * d.z * aYu), 0.f);
 		}
+	}
 	}
 }
 
