@@ -67,7 +67,8 @@ template <int RB> struct SFwdCfg {
 	static constexpr size_t O_LIVE = O_MASK + 4 * 8 * (SFB / 32);
 	static constexpr size_t O_FLAG = O_LIVE + 4 * 4;               // u32 [SFB]: bit r = blended into a pixel of row r
 	static constexpr size_t O_LOC = O_FLAG + 4 * SFB;
-	static constexpr size_t BYTES = O_LOC + 4 * (LGS_NB + 1);
+	static constexpr size_t O_STATE = (O_LOC + 4 * (LGS_NB + 1) + 15) / 16 * 16; // per pixel blend state between batches: 13 words [NPG * 32] each
+	static constexpr size_t BYTES = O_STATE + 4 * 13 * 32 * NPG;
 };
 
 template <int RB>
@@ -94,6 +95,10 @@ surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 	unsigned *slive = reinterpret_cast<unsigned *>(smem + C::O_LIVE);
 	unsigned *sflag = reinterpret_cast<unsigned *>(smem + C::O_FLAG);
 	unsigned *sloc = reinterpret_cast<unsigned *>(smem + C::O_LOC);
+	// The per-pixel accumulators live in shared memory between batches (13 words per pixel): the evaluate phase, which
+	// every warp runs, then has the registers for two interleaved pair evaluations.
+	float *sst = reinterpret_cast<float *>(smem + C::O_STATE);
+	constexpr int SS = 32 * NPG; // stride between the 13 state planes
 
 	const int bin = (int)order[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int tx = bin % g.gx, rg = bin / g.gx;
@@ -101,14 +106,13 @@ surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 	for (int i = tid; i < LGS_NB; i += NT) sloc[i] = loc[(size_t)bin * LGS_NB + i];
 	if (tid == 0) sloc[LGS_NB] = ntotal;
 	if (tid < B) sflag[tid] = 0;
+	for (int i = tid; i < 13 * SS; i += NT) sst[i] = (i < SS) ? 1.0f : 0.f; // plane 0 = T = 1; everything else 0
 
 	// blend state: warp w < NPG owns pixel group w, lane = pixel (row 2w + lane / 16, column lane % 16)
 	const bool blender = warp < NPG;
 	const int brow = 2 * warp + (lane >> 4), bcol = lane & 15; // row inside the bin
 	const int px = tx * LGS_TILE_X_ + bcol, py = rg * RB + brow;
 	const bool inside = blender && px < g.W && py < g.H && brow < RB;
-	float T = 1.0f, C0 = 0.f, C1 = 0.f, D = 0.f, M1 = 0.f, M2 = 0.f, dist = 0.f, Nx = 0.f, Ny = 0.f, Nz = 0.f, med_depth = 0.f;
-	unsigned last = 0, medpos = 0;
 	bool done = !inside;
 	if (blender) {
 		PixelRay ray = {0.f, 0.f, 0.f};
@@ -236,15 +240,19 @@ surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 							en.lambda = ee.x; en.ruu = ee.y; en.rvv = ee.z;
 							float amax = 0.f;
 							unsigned l2 = lv;
-							while (l2) {
-								const int p = __ffs(l2) - 1;
+							while (l2) { // two live pixels per trip: two independent dependency chains per lane
+								const int p0 = __ffs(l2) - 1;
 								l2 &= l2 - 1;
-								const float4 rr = rays[p];
-								float alpha = 0.f, depth = 0.f;
-								if (valid) alpha = surfel_pair<false>(rr.x, rr.y, rr.z, (float)(tx * LGS_TILE_X_ + p), erowf, q0, q1, q2, q3, q4, en, depth, nullptr);
-								ta[p * LD + kk] = alpha;
-								td[p * LD + kk] = depth;
-								amax = fmaxf(amax, alpha);
+								const int p1 = l2 ? __ffs(l2) - 1 : p0; // odd count: the last pixel is evaluated twice (same value, same slot)
+								l2 &= l2 - 1;
+								const float4 r0 = rays[p0], r1 = rays[p1];
+								float d0, d1;
+								float a0 = surfel_pair_nb(r0.x, r0.y, r0.z, (float)(tx * LGS_TILE_X_ + p0), erowf, q0, q1, q2, q3, q4, en, d0);
+								float a1 = surfel_pair_nb(r1.x, r1.y, r1.z, (float)(tx * LGS_TILE_X_ + p1), erowf, q0, q1, q2, q3, q4, en, d1);
+								if (!valid) { a0 = 0.f; a1 = 0.f; }
+								ta[p0 * LD + kk] = a0; td[p0 * LD + kk] = d0;
+								ta[p1 * LD + kk] = a1; td[p1 * LD + kk] = d1;
+								amax = fmaxf(amax, fmaxf(a0, a1));
 							}
 							m32 = __ballot_sync(0xffffffffu, amax != 0.f);
 						}
@@ -264,6 +272,10 @@ surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 				if (blender) {
 					// ---------------- blend: lanes = pixels, each half-warp walks its own row's list (fwd.cu:487-522) ----------------
 					if (!__all_sync(0xffffffffu, done)) {
+						float *sp = sst + warp * 32 + lane;
+						float T = sp[0], C0 = sp[SS], C1 = sp[2 * SS], D = sp[3 * SS], M1 = sp[4 * SS], M2 = sp[5 * SS], dist = sp[6 * SS],
+						      Nx = sp[7 * SS], Ny = sp[8 * SS], Nz = sp[9 * SS], med_depth = sp[10 * SS];
+						unsigned last = __float_as_uint(sp[11 * SS]), medpos = __float_as_uint(sp[12 * SS]);
 						const int r1 = RB >= 2 ? 2 * warp + 1 : 0;
 						const unsigned mycnt = brow < RB ? scnt[brow] : 0u;
 						const float *ta = tileA + (size_t)(brow < RB ? brow : 0) * (C::ROWTILE / 4) + bcol * LD;
@@ -300,6 +312,9 @@ surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 								atomicOr(&sflag[j], 1u << brow); // the backward pass only revisits (entry, row) pairs that blended
 							}
 						}
+						sp[0] = T; sp[SS] = C0; sp[2 * SS] = C1; sp[3 * SS] = D; sp[4 * SS] = M1; sp[5 * SS] = M2; sp[6 * SS] = dist;
+						sp[7 * SS] = Nx; sp[8 * SS] = Ny; sp[9 * SS] = Nz; sp[10 * SS] = med_depth;
+						sp[11 * SS] = __uint_as_float(last); sp[12 * SS] = __uint_as_float(medpos);
 					}
 					const unsigned lvn = __ballot_sync(0xffffffffu, !done);
 					if (lane == 0) slive[warp] = lvn;
@@ -329,7 +344,12 @@ surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 		if (all_done && !sort_all) break;
 	}
 	if (tid == 0) sorted_end[bin] = (k < LGS_NB) ? sloc[k] : ntotal;
+	__syncthreads();
 	if (inside) {
+		const float *sp = sst + warp * 32 + lane;
+		const float T = sp[0], C0 = sp[SS], C1 = sp[2 * SS], D = sp[3 * SS], M1 = sp[4 * SS], dist = sp[6 * SS],
+			    Nx = sp[7 * SS], Ny = sp[8 * SS], Nz = sp[9 * SS], med_depth = sp[10 * SS];
+		const unsigned last = __float_as_uint(sp[11 * SS]), medpos = __float_as_uint(sp[12 * SS]);
 		const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
 		final_T[pix] = T;
 		n_contrib[pix] = last;
@@ -513,14 +533,16 @@ surfel_render_bwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 					SurfelEntry en;
 					en.lambda = ee.x; en.ruu = ee.y; en.rvv = ee.z;
 					float amax = 0.f;
-					for (int p = 0; p < 16; p++) {
-						const float4 rr = sray[16 * h + p]; // .w = the pixel's last contributor
-						float alpha = 0.f, depth = 0.f;
-						if (rowok && qe.z < __float_as_uint(rr.w))
-							alpha = surfel_pair<false>(rr.x, rr.y, rr.z, (float)(tx * LGS_TILE_X_ + p), (float)row, q0, q1, q2, q3, q4, en, depth, nullptr);
-						ta[p * LD] = alpha;
-						td[p * LD] = depth;
-						amax = fmaxf(amax, alpha);
+					for (int p = 0; p < 16; p += 2) { // two pixels per trip: two independent dependency chains per lane
+						const float4 r0 = sray[16 * h + p], r1 = sray[16 * h + p + 1]; // .w = the pixel's last contributor
+						float d0 = 0.f, d1 = 0.f;
+						float a0 = surfel_pair_nb(r0.x, r0.y, r0.z, (float)(tx * LGS_TILE_X_ + p), (float)row, q0, q1, q2, q3, q4, en, d0);
+						float a1 = surfel_pair_nb(r1.x, r1.y, r1.z, (float)(tx * LGS_TILE_X_ + p + 1), (float)row, q0, q1, q2, q3, q4, en, d1);
+						if (!(rowok && qe.z < __float_as_uint(r0.w))) a0 = 0.f;
+						if (!(rowok && qe.z < __float_as_uint(r1.w))) a1 = 0.f;
+						ta[p * LD] = a0; ta[(p + 1) * LD] = a1;
+						td[p * LD] = d0; td[(p + 1) * LD] = d1;
+						amax = fmaxf(amax, fmaxf(a0, a1));
 					}
 					m32 = __ballot_sync(0xffffffffu, amax != 0.f);
 				}
