@@ -36,6 +36,13 @@ CASES = {
     "gs5_dense_terminate": dict(P=6000, H=4, W=64, seed=25, pose="identity", scale_range=(0.1, 0.6),
                                 opacity_range=(0.5, 1.0)),
     "gs6_depth_ties": dict(P=1500, H=8, W=96, seed=26, opacity_range=(0.3, 0.9), scale_range=(0.1, 0.5), duplicate=True),
+    # thousands of entries in ONE depth bucket of every bin (in-place global bitonic sort, multi-chunk segments), opacities
+    # straddling the alpha < 1/255 skip: threshold-adversarial for a CPU libm (`adversarial` flag)
+    "gs7_monster_bucket": dict(P=6000, H=8, W=64, seed=27, scale_range=(0.3, 1.5), range_m=(10.0, 10.5),
+                               opacity_range=(0.003, 0.03), adversarial=True),
+    # big near discs: axis end points cross the azimuth seam, extents of hundreds of columns, rects over every bin of a row
+    "gs8_seam_wrap": dict(P=2500, H=16, W=256, seed=28, pose="random", scale_range=(0.5, 2.5), range_m=(2.0, 30.0),
+                          opacity_range=(0.05, 0.6)),
 }
 
 
@@ -104,6 +111,7 @@ def run_ref(ref, sc, dev, with_bwd=True, d=None):
 def build_case(kw):
     kw = dict(kw)
     duplicate = kw.pop("duplicate", False)
+    kw.pop("adversarial", None)
     near = kw.pop("near", 0)
     mod = kw.pop("scale_modifier", 1.0)
     sc = synth.make_surfel_scene(**kw)
@@ -123,12 +131,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/goldens_surfel")
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated case names (default: all)")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     ref = build_ref.load_surfel()
     assert ref is not None, "oracle/_ref/lidargs_surfel_ref_C.so missing: run oracle/build_ref.py where /root/reference exists"
     dev = torch.device("cuda:0")
     for name, kw in CASES.items():
+        if a.only and name not in a.only.split(","):
+            continue
         sc = build_case(kw)
         runs = [run_ref(ref, sc, dev) for _ in range(3)]
         r0 = runs[0]
@@ -138,7 +149,7 @@ def main():
         R = r0["R"]
         pl = r0["binning"].cpu().numpy()[:4 * R].view(np.uint32).copy()
         out = {("in_" + k): v for k, v in sc.items() if isinstance(v, np.ndarray)}
-        out.update(in_far=sc["far"], in_near=sc["near"], in_scale_modifier=sc["scale_modifier"], in_H=H, in_W=W,
+        out.update(adversarial=bool(kw.get("adversarial", False)), in_far=sc["far"], in_near=sc["near"], in_scale_modifier=sc["scale_modifier"], in_H=H, in_W=W,
                    in_tanfovx=sc["tanfovx"], in_tanfovy=sc["tanfovy"])
         out.update(num_rendered=R, color=r0["color"].cpu().numpy(), others=r0["others"].cpu().numpy(),
                    radii=r0["radii"].cpu().numpy())
