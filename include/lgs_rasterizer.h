@@ -185,6 +185,32 @@ int lgs_grad_scatter_add(int P, const float *gathered, int nranks, int my_rank, 
                          float *dL_dmean3D, float *dL_dscale, float *dL_drot,
                          float *dL_dopacity, float *dL_dcolor, void *stream);
 
+/* ==== neural-Gaussian decode (the caller-side step in front of the rasterizer) =========
+ * Fused replacement of gaussian_renderer/__init__.py:17-119 generate_neural_gaussians for the default model
+ * configuration (use_feat_bank = False, appearance_dim = 0, color_channel = 2, feat_dim = 32): four MLPs
+ * Linear(35|36, 32) + ReLU + Linear(32, K | 7K | K | K) (scene/gaussian_model.py:114-141), opacity > 0 mask, compaction.
+ * MLP order in lgs_decode_weights: 0 opacity, 1 cov, 2 color, 3 raydrop; w1 [32, in_dim] and w2 [out, 32] row-major
+ * exactly as nn.Linear stores them; in_dim = 36 with the distance input, 35 without (add_*_dist flags).
+ * Two calls because the host needs the survivor count M to size the outputs:
+ *   lgs_decode_count : neural_opacity [Av*K], mask [Av*K] (bytes), survivor counts + scan into `scratch`
+ *                      (lgs_decode_scratch_bytes(Av)); *total_dev = device address of M (uint32)
+ *   lgs_decode_write : xyz [M,3], color [M,2] (intensity, ray-drop), opacity [M], scaling [M,3], rot [M,4]
+ * vis_idx (int64 [Av], indices of the visible anchors in ascending order) may be NULL = all anchors.
+ * `scaling` is the ACTIVATED anchor scaling [A,6] (pc.get_scaling).
+ */
+typedef struct lgs_decode_weights {
+	const float *w1[4], *b1[4], *w2[4], *b2[4];
+	int in_dim[4];
+} lgs_decode_weights;
+size_t lgs_decode_scratch_bytes(int Av);
+int lgs_decode_count(int Av, int K, const long long *vis_idx, const float *feat, const float *anchor,
+                     const float *cam_center, const lgs_decode_weights *w, float *neural_opacity,
+                     unsigned char *mask, char *scratch, uint32_t **total_dev, void *stream);
+int lgs_decode_write(int Av, int K, const long long *vis_idx, const float *feat, const float *anchor,
+                     const float *offset, const float *scaling, const float *cam_center,
+                     const lgs_decode_weights *w, const float *neural_opacity, const char *scratch,
+                     float *xyz, float *color, float *opacity, float *scaling_out, float *rot, void *stream);
+
 /* ---- knobs and introspection (no reference counterpart) -------------------------------- */
 
 /* Rows of 16x1 tiles that share one depth-binned list (1, 2, 4, 8 or 16; 0 = auto). */
