@@ -211,6 +211,23 @@ int lgs_decode_write(int Av, int K, const long long *vis_idx, const float *feat,
                      const lgs_decode_weights *w, const float *neural_opacity, const char *scratch,
                      float *xyz, float *color, float *opacity, float *scaling_out, float *rot, void *stream);
 
+/*
+ * Backward of the decode (what autograd does through gaussian_renderer/__init__.py:17-119 in training): upstream
+ * gradients of the five compacted outputs (and optionally of neural_opacity, may be NULL) -> d_feat [A,32],
+ * d_anchor [A,3], d_offset [A,K,3], d_scaling [A,6] (rows of visible anchors are written, the caller zero-fills the
+ * rest) and the MLP weight gradients, ADDED into dW: one flat zero-initialised array of lgs_decode_weight_floats(K)
+ * floats laid out per MLP (order opacity, cov, color, raydrop) as w1 [32][36] (columns >= in_dim unused), b1 [32],
+ * w2 [outs][32], b2 [outs rounded up to a multiple of 4].  `scratch` / `neural_opacity` are the forward's.  K <= 10.
+ */
+size_t lgs_decode_weight_floats(int K);
+int lgs_decode_backward(int Av, int K, const long long *vis_idx, const float *feat, const float *anchor,
+                        const float *offset, const float *scaling, const float *cam_center,
+                        const lgs_decode_weights *w, const float *neural_opacity, const char *scratch,
+                        const float *g_xyz, const float *g_color, const float *g_opacity,
+                        const float *g_scaling, const float *g_rot, const float *g_neural_opacity,
+                        float *d_feat, float *d_anchor, float *d_offset, float *d_scaling, float *dW,
+                        void *stream);
+
 /* ---- knobs and introspection (no reference counterpart) -------------------------------- */
 
 /* Rows of 16x1 tiles that share one depth-binned list (1, 2, 4, 8 or 16; 0 = auto). */

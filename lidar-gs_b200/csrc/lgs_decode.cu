@@ -242,6 +242,206 @@ decode_write_kernel(int Av, int K, const long long *__restrict__ vis_idx, const 
 	}
 }
 
+// ---- backward -------------------------------------------------------------------------------------------------------
+// One tile = the DEC_NT anchors of a forward block (same survivor-row mapping).  Phase A, one thread per anchor:
+// recompute the forward, turn the upstream gradients of the survivors into pre-activation gradients, back-propagate
+// to the MLP input (-> d feat, d anchor) and park X, H, dZ1, dZ2 of the tile in shared memory.  Phase B, all threads:
+// the weight gradients of the tile are four small GEMMs over the tile's anchors (dW1 = dZ1^T X, dW2 = dZ2^T H),
+// accumulated in a shared-memory copy of the weight layout; a persistent block adds it to global memory once.
+#define DBW_NT 256
+#define DBW_XS 37 // row strides that keep the per-anchor stores conflict-free
+#define DBW_HS 33
+
+// floats of the shared-memory weight layout of decode_load_weights (per MLP: w1 [32][36], b1 [32], w2 [outs][32], b2 [outs -> x4])
+static size_t decode_weight_floats(int K) { return 4 * (DEC_HID * DEC_IN + DEC_HID) + 10 * K * DEC_HID + 3 * ((K + 3) & ~3) + ((7 * K + 3) & ~3); }
+static size_t decode_bwd_smem_bytes(int K)
+{
+	return sizeof(float) * (2 * decode_weight_floats(K) + DEC_NT * (DBW_XS + 2 * DBW_HS + (7 * K + 1)) + 16);
+}
+
+__global__ void __launch_bounds__(DBW_NT, 1)
+decode_backward_kernel(int Av, int K, int ntiles, const long long *__restrict__ vis_idx, const float *__restrict__ feat,
+		       const float *__restrict__ anchor, const float *__restrict__ offset, const float *__restrict__ scaling,
+		       const float *__restrict__ cam, lgs_decode_weights w, const float *__restrict__ neural_opacity,
+		       const uint32_t *__restrict__ counts, const uint32_t *__restrict__ block_base, const float *__restrict__ g_xyz,
+		       const float *__restrict__ g_color, const float *__restrict__ g_opacity, const float *__restrict__ g_scaling,
+		       const float *__restrict__ g_rot, const float *__restrict__ g_nop, float *__restrict__ d_feat,
+		       float *__restrict__ d_anchor, float *__restrict__ d_offset, float *__restrict__ d_scaling,
+		       float *__restrict__ dW, int wfloats)
+{
+	extern __shared__ __align__(16) float dsm[];
+	__shared__ unsigned wsum[DEC_NT / 32];
+	const DecodeSmem s = decode_load_weights(dsm, w, K, 0xfu);
+	float *sdW = dsm + wfloats;
+	float *X = sdW + wfloats, *H = X + DEC_NT * DBW_XS, *Z1 = H + DEC_NT * DBW_HS, *Z2 = Z1 + DEC_NT * DBW_HS;
+	const int ZS = 7 * K + 1;
+	const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+	const int outs[4] = {K, 7 * K, K, K};
+	for (int i = tid; i < wfloats; i += DBW_NT) sdW[i] = 0.f;
+	__syncthreads();
+
+	for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		const int v = tile * DEC_NT + tid;
+		const bool worker = tid < DEC_NT, live = worker && v < Av;
+		// survivor row of this anchor (same arithmetic as decode_write_kernel)
+		const unsigned cnt = live ? counts[v] : 0;
+		unsigned x_ = cnt;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const unsigned y = __shfl_up_sync(0xffffffffu, x_, o);
+			if (lane >= o) x_ += y;
+		}
+		if (worker && lane == 31) wsum[wp] = x_;
+		__syncthreads();
+		unsigned row = 0;
+		if (worker) {
+			row = block_base[tile] + x_ - cnt;
+			for (int i = 0; i < wp; i++) row += wsum[i];
+		}
+		float x[DEC_IN], dx[DEC_IN], sc[6], dsc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dan[3] = {0.f, 0.f, 0.f};
+		size_t a = 0;
+		unsigned surv = 0;
+#pragma unroll
+		for (int i = 0; i < DEC_IN; i++) { x[i] = 0.f; dx[i] = 0.f; }
+		if (live) {
+			a = vis_idx ? (size_t)vis_idx[v] : (size_t)v;
+			decode_input(feat, anchor, cam, a, x);
+#pragma unroll
+			for (int i = 0; i < 6; i++) sc[i] = scaling[6 * a + i];
+			for (int k = 0; k < K; k++) surv |= (neural_opacity[(size_t)v * K + k] > 0.0f ? 1u : 0u) << k;
+		}
+		if (worker) {
+#pragma unroll
+			for (int i = 0; i < DEC_IN; i++) X[tid * DBW_XS + i] = x[i];
+		}
+		for (int m = 0; m < 4; m++) {
+			if (worker) {
+				float h[DEC_HID], dh[DEC_HID];
+#pragma unroll
+				for (int j = 0; j < DEC_HID; j++) { h[j] = 0.f; dh[j] = 0.f; }
+				if (live) decode_hidden(s.w1[m], s.b1[m], x, h);
+				unsigned r = row;
+				for (int k = 0; k < K; k++) {
+					const bool sv = (surv >> k) & 1u;
+					if (m == 1) { // covariance MLP: 3 scale logits + quaternion per offset (__init__.py:93-111)
+						float z[7], dz[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+						if (live && sv) {
+#pragma unroll
+							for (int c = 0; c < 7; c++) z[c] = decode_out(s.w2[1], s.b2[1], 7 * k + c, h);
+#pragma unroll
+							for (int c = 0; c < 3; c++) {
+								const float sg = decode_sigmoid(z[c]), gs = g_scaling[3 * (size_t)r + c];
+								dz[c] = gs * sc[3 + c] * sg * (1.f - sg);
+								dsc[3 + c] += gs * sg;
+							}
+							const float qn = fmaxf(sqrtf(z[3] * z[3] + z[4] * z[4] + z[5] * z[5] + z[6] * z[6]), 1e-12f);
+							const float4 gr = reinterpret_cast<const float4 *>(g_rot)[r];
+							const float q0 = z[3] / qn, q1 = z[4] / qn, q2 = z[5] / qn, q3 = z[6] / qn;
+							const float dt = q0 * gr.x + q1 * gr.y + q2 * gr.z + q3 * gr.w;
+							dz[3] = (gr.x - q0 * dt) / qn; dz[4] = (gr.y - q1 * dt) / qn;
+							dz[5] = (gr.z - q2 * dt) / qn; dz[6] = (gr.w - q3 * dt) / qn;
+							// centres: xyz = anchor + offset * scaling[:3] (:114-115)
+							const float *of = offset + (a * K + k) * 3;
+#pragma unroll
+							for (int c = 0; c < 3; c++) {
+								const float gx = g_xyz[3 * (size_t)r + c];
+								d_offset[(a * K + k) * 3 + c] = gx * sc[c];
+								dsc[c] += gx * of[c];
+								dan[c] += gx;
+							}
+						}
+#pragma unroll
+						for (int c = 0; c < 7; c++) {
+							Z2[tid * ZS + 7 * k + c] = dz[c];
+							if (dz[c] != 0.f) {
+								const float *wr = s.w2[1] + (7 * k + c) * DEC_HID;
+#pragma unroll
+								for (int j = 0; j < DEC_HID; j++) dh[j] = fmaf(wr[j], dz[c], dh[j]);
+							}
+						}
+					} else {
+						float dz = 0.f;
+						if (live) {
+							if (m == 0) { // opacity = tanh(z) (:60-71); neural_opacity itself may carry a gradient too
+								const float o = neural_opacity[(size_t)v * K + k];
+								float gsum = g_nop ? g_nop[(size_t)v * K + k] : 0.f;
+								if (sv) gsum += g_opacity[r];
+								dz = gsum * (1.f - o * o);
+							} else if (sv) { // colour (m == 2) / ray-drop (m == 3): sigmoid (:83-90)
+								const float sg = decode_sigmoid(decode_out(s.w2[m], s.b2[m], k, h));
+								dz = g_color[2 * (size_t)r + (m == 2 ? 0 : 1)] * sg * (1.f - sg);
+							}
+						}
+						Z2[tid * ZS + k] = dz;
+						if (dz != 0.f) {
+							const float *wr = s.w2[m] + k * DEC_HID;
+#pragma unroll
+							for (int j = 0; j < DEC_HID; j++) dh[j] = fmaf(wr[j], dz, dh[j]);
+						}
+					}
+					r += sv;
+				}
+#pragma unroll
+				for (int j = 0; j < DEC_HID; j++) {
+					const float d1 = h[j] > 0.f ? dh[j] : 0.f; // ReLU
+					H[tid * DBW_HS + j] = h[j];
+					Z1[tid * DBW_HS + j] = d1;
+					if (d1 != 0.f) {
+						const float *wr = s.w1[m] + j * DEC_IN;
+#pragma unroll
+						for (int i = 0; i < DEC_IN; i++) dx[i] = fmaf(wr[i], d1, dx[i]);
+					}
+				}
+			}
+			__syncthreads();
+			// ---- phase B: weight gradients of this MLP over the tile ----
+			{
+				float *gW1 = sdW + (s.w1[m] - dsm), *gb1 = sdW + (s.b1[m] - dsm), *gW2 = sdW + (s.w2[m] - dsm), *gb2 = sdW + (s.b2[m] - dsm);
+				for (int o = tid; o < DEC_HID * DEC_IN; o += DBW_NT) {
+					const int j = o / DEC_IN, i = o - j * DEC_IN;
+					float acc = 0.f;
+#pragma unroll 8
+					for (int n = 0; n < DEC_NT; n++) acc = fmaf(Z1[n * DBW_HS + j], X[n * DBW_XS + i], acc);
+					gW1[o] += acc;
+				}
+				for (int o = tid; o < outs[m] * DEC_HID; o += DBW_NT) {
+					const int o2 = o / DEC_HID, j = o - o2 * DEC_HID;
+					float acc = 0.f;
+#pragma unroll 8
+					for (int n = 0; n < DEC_NT; n++) acc = fmaf(Z2[n * ZS + o2], H[n * DBW_HS + j], acc);
+					gW2[o] += acc;
+				}
+				if (tid < DEC_HID) {
+					float acc = 0.f;
+					for (int n = 0; n < DEC_NT; n++) acc += Z1[n * DBW_HS + tid];
+					gb1[tid] += acc;
+				} else if (tid >= 64 && tid - 64 < outs[m]) {
+					float acc = 0.f;
+					for (int n = 0; n < DEC_NT; n++) acc += Z2[n * ZS + tid - 64];
+					gb2[tid - 64] += acc;
+				}
+			}
+			__syncthreads();
+		}
+		if (live) {
+			float4 *df = reinterpret_cast<float4 *>(d_feat + a * DEC_FEAT);
+#pragma unroll
+			for (int i = 0; i < DEC_FEAT / 4; i++) df[i] = make_float4(dx[4 * i], dx[4 * i + 1], dx[4 * i + 2], dx[4 * i + 3]);
+			// view = ob / |ob|, dist = |ob|, ob = anchor - cam (:29-35)
+			const float dist = x[35], dv = x[32] * dx[32] + x[33] * dx[33] + x[34] * dx[34];
+#pragma unroll
+			for (int c = 0; c < 3; c++) d_anchor[3 * a + c] = dan[c] + (dx[32 + c] - x[32 + c] * dv) / dist + x[32 + c] * dx[35];
+#pragma unroll
+			for (int i = 0; i < 6; i++) d_scaling[6 * a + i] = dsc[i];
+		}
+	}
+	__syncthreads();
+	for (int i = tid; i < wfloats; i += DBW_NT) {
+		const float g = sdW[i];
+		if (g != 0.f) atomicAdd(dW + i, g);
+	}
+}
+
 bool decode_args_ok(int Av, int K, const lgs_decode_weights *w)
 {
 	if (Av < 0 || K < 1 || K > DEC_MAXK || !w) return false;
@@ -302,6 +502,34 @@ int lgs_decode_write(int Av, int K, const long long *vis_idx, const float *feat,
 	decode_write_kernel<<<nb, DEC_NT, decode_smem_bytes(K), (cudaStream_t)stream>>>(Av, K, vis_idx, feat, anchor, offset, scaling,
 											 cam_center, *w, neural_opacity, counts, bsums, xyz,
 											 color, opacity, scaling_out, rot);
+	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;
+}
+
+size_t lgs_decode_weight_floats(int K) { return decode_weight_floats(K); }
+
+int lgs_decode_backward(int Av, int K, const long long *vis_idx, const float *feat, const float *anchor, const float *offset,
+			const float *scaling, const float *cam_center, const lgs_decode_weights *w, const float *neural_opacity,
+			const char *scratch, const float *g_xyz, const float *g_color, const float *g_opacity, const float *g_scaling,
+			const float *g_rot, const float *g_neural_opacity, float *d_feat, float *d_anchor, float *d_offset,
+			float *d_scaling, float *dW, void *stream)
+{
+	if (!decode_args_ok(Av, K, w) || K > 10) return LGS_EINVAL;
+	if (Av == 0) return 0;
+	if (!feat || !anchor || !offset || !scaling || !cam_center || !neural_opacity || !scratch || !d_feat || !d_anchor || !d_offset ||
+	    !d_scaling || !dW)
+		return LGS_EINVAL;
+	const int nb = (Av + DEC_NT - 1) / DEC_NT;
+	const uint32_t *counts = (const uint32_t *)scratch;
+	const uint32_t *bsums = (const uint32_t *)(scratch + lgs_al((size_t)Av * 4));
+	static bool configured = false;
+	if (!configured) {
+		cudaFuncSetAttribute(decode_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_bwd_smem_bytes(10));
+		configured = true;
+	}
+	const int grid = nb < 148 ? nb : 148;
+	decode_backward_kernel<<<grid, DBW_NT, decode_bwd_smem_bytes(K), (cudaStream_t)stream>>>(
+		Av, K, nb, vis_idx, feat, anchor, offset, scaling, cam_center, *w, neural_opacity, counts, bsums, g_xyz, g_color, g_opacity,
+		g_scaling, g_rot, g_neural_opacity, d_feat, d_anchor, d_offset, d_scaling, dW, (int)decode_weight_floats(K));
 	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;
 }
 

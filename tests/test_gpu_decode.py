@@ -105,11 +105,63 @@ def test_generate_neural_gaussians_signature_and_guards():
         seven = ng.generate_neural_gaussians(Cam, PC, t(p["visible"]), is_training=True)
     assert len(five) == 5 and len(seven) == 7
     _compare([o.cpu().numpy() for o in seven], [g[n] for n in NAMES], "generate_neural_gaussians")
-    PC._anchor_feat = PC._anchor_feat.clone().requires_grad_(True)
-    with pytest.raises(NotImplementedError, match="forward-only"):
-        ng.generate_neural_gaussians(Cam, PC, t(p["visible"]), is_training=True)
     PC.use_feat_bank = True
     with pytest.raises(NotImplementedError):
         ng.generate_neural_gaussians(Cam, PC, None)
     with pytest.raises(RuntimeError, match="CUDA"):
         ng.decode(torch.zeros(4, 32), torch.zeros(4, 3), torch.zeros(4, 6, 3), torch.ones(4, 6), torch.zeros(3), m)
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[p.split("/")[-1][:-4] for p in GOLD])
+def test_decode_backward_matches_reference_autograd(path):
+    """Gradients of the fixed random loss of the golden (sum of outputs x upstream) w.r.t. anchors, features, offsets,
+    log-scaling and all sixteen MLP tensors, against torch.autograd through the reference's own function."""
+    from lgs_b200 import neural_gaussians as ng
+    p, g = load_decode_golden(path)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    leaves = dict(anchor=t(p["anchor"]).requires_grad_(True), feat=t(p["feat"]).requires_grad_(True),
+                  offset=t(p["offset"]).requires_grad_(True), log_scaling=t(p["log_scaling"]).requires_grad_(True))
+    mlps = _mlps(p, dev)
+    vis = t(p["visible"]) if p.get("visible") is not None else None
+    out = ng.decode(leaves["feat"], leaves["anchor"], leaves["offset"], 1.0 * torch.exp(leaves["log_scaling"]), t(p["cam_center"]),
+                    mlps, vis)
+    assert out[0].requires_grad and not out[6].requires_grad
+    _compare([o.detach().cpu().numpy() for o in out], [g[n] for n in NAMES], path)
+    ups = [t(g["up_" + n]) for n in ("xyz", "color", "opacity", "scaling", "rot")]
+    loss = sum((o * u).sum() for o, u in zip(out[:5], ups))
+    loss.backward()
+    torch.cuda.synchronize()
+    for n, leaf in leaves.items():
+        ref = g["grad_" + n]
+        assert util.rel_norm(leaf.grad.cpu().numpy(), ref) < 1e-4, (n, util.rel_norm(leaf.grad.cpu().numpy(), ref))
+    for name in ("opacity", "cov", "color", "raydrop"):
+        lin = [m for m in mlps[name] if isinstance(m, torch.nn.Linear)]
+        for key, prm in (("w1", lin[0].weight), ("b1", lin[0].bias), ("w2", lin[1].weight), ("b2", lin[1].bias)):
+            ref = g[f"grad_{name}_{key}"]
+            got = prm.grad.cpu().numpy()
+            assert got.shape == ref.shape, (name, key)
+            assert util.rel_norm(got, ref) < 1e-4, (name, key, util.rel_norm(got, ref))
+
+
+def test_decode_backward_with_neural_opacity_gradient_and_partial_upstream():
+    """neural_opacity (the un-masked [Av*K, 1] output) may itself feed a loss; unused outputs get no upstream gradient."""
+    from lgs_b200 import neural_gaussians as ng
+    p, g = load_decode_golden(GOLD[1])
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    feat = t(p["feat"]).requires_grad_(True)
+    mlps = _mlps(p, dev)
+    vis = t(p["visible"])
+    out = ng.decode(feat, t(p["anchor"]), t(p["offset"]), t(p["scaling"]), t(p["cam_center"]), mlps, vis)
+    (out[5].sum() + out[2].sum()).backward()  # d/dfeat of sum(tanh) over all offsets + over the survivors again
+    got = feat.grad.cpu().numpy()
+    # reference: eager PyTorch of the opacity branch only
+    f2 = t(p["feat"]).requires_grad_(True)
+    anchor, cam = t(p["anchor"]), t(p["cam_center"])
+    ob = anchor[vis] - cam
+    d = ob.norm(dim=1, keepdim=True)
+    x = torch.cat([f2[vis], ob / d, d], 1)
+    no = mlps["opacity"](x).reshape(-1, 1)
+    (no.sum() + no[no.view(-1) > 0].sum()).backward()
+    assert util.rel_norm(got, f2.grad.cpu().numpy()) < 1e-4
