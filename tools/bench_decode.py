@@ -61,9 +61,46 @@ with torch.no_grad():
     err = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(out[:5], ref)) if ref[0].shape[0] == M else float("nan")
     ms_fused = timeit(lambda: ng.decode(feat, anchor, offset, scaling, cam, mlps))
     ms_eager = timeit(eager)
+# ---- training step: forward + backward through the decode (loss = fixed random projection of the five outputs) ----
+leaves = [t.clone().requires_grad_(True) for t in (feat, anchor, offset, scaling)]
+ups = None
+
+
+def train_fused():
+    global ups
+    for t in leaves:
+        t.grad = None
+    for m in mlps.values():
+        m.zero_grad(set_to_none=True)
+    out = ng.decode(leaves[0], leaves[1], leaves[2], leaves[3], cam, mlps)
+    if ups is None:
+        gg = torch.Generator(device="cpu").manual_seed(9)
+        ups = [torch.randn(o.shape, generator=gg).to(dev) for o in out[:5]]
+    torch.autograd.backward(list(out[:5]), ups)
+
+
+def train_eager():
+    global feat, anchor, offset, scaling
+    for t in leaves:
+        t.grad = None
+    for m in mlps.values():
+        m.zero_grad(set_to_none=True)
+    feat, anchor, offset, scaling = leaves
+    out = eager()
+    torch.autograd.backward(list(out), ups)
+
+
+train_fused()
+g_fused = [t.grad.clone() for t in leaves] + [prm.grad.clone() for m in mlps.values() for prm in m.parameters()]
+train_eager()
+g_eager = [t.grad.clone() for t in leaves] + [prm.grad.clone() for m in mlps.values() for prm in m.parameters()]
+gerr = max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) for a, b in zip(g_fused, g_eager))
+ms_train_fused, ms_train_eager = timeit(train_fused, 10), timeit(train_eager, 10)
+feat, anchor, offset, scaling = [t.detach() for t in leaves]
 alg = A * (128 + 12 + 72 + 24) + A * K * 5 + M * 52  # inputs once, neural_opacity + mask, compacted outputs
 line = dict(op="neural-Gaussian decode (forward)", A=A, K=K, M=M, ms_fused=ms_fused, ms_eager_pytorch=ms_eager,
             speedup_vs_eager=ms_eager / ms_fused, max_rel_err_vs_eager=err, algorithmic_bytes=alg,
-            gbs=alg / (ms_fused * 1e-3) / 1e9, note="fused = 2 kernels + scan + one host read of M; eager = PyTorch restatement of "
+            gbs=alg / (ms_fused * 1e-3) / 1e9, ms_fwd_bwd_fused=ms_train_fused, ms_fwd_bwd_eager_pytorch=ms_train_eager,
+            speedup_fwd_bwd=ms_train_eager / ms_train_fused, max_rel_grad_err_vs_eager=gerr, note="fused = 2 kernels + scan + one host read of M; eager = PyTorch restatement of "
             "gaussian_renderer/__init__.py:17-119 (stand-in for the reference function, which cannot travel to the GPU box)")
 print(json.dumps(line))
