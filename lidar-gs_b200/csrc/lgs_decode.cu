@@ -96,6 +96,18 @@ __device__ __forceinline__ float decode_out(const float *__restrict__ w2, const 
 	return acc;
 }
 __device__ __forceinline__ float decode_sigmoid(float z) { return 1.0f / (1.0f + expf(-z)); }
+// y[0..N) += a * row[0..N): one weight row (16-byte aligned in shared memory) read as float4 broadcasts
+template <int N>
+__device__ __forceinline__ void decode_axpy(const float *__restrict__ row, float a, float *y)
+{
+	const float4 *r = reinterpret_cast<const float4 *>(row);
+#pragma unroll
+	for (int i = 0; i < N / 4; i++) {
+		const float4 w = r[i];
+		y[4 * i] = fmaf(w.x, a, y[4 * i]); y[4 * i + 1] = fmaf(w.y, a, y[4 * i + 1]);
+		y[4 * i + 2] = fmaf(w.z, a, y[4 * i + 2]); y[4 * i + 3] = fmaf(w.w, a, y[4 * i + 3]);
+	}
+}
 
 __global__ void __launch_bounds__(DEC_NT)
 decode_opacity_kernel(int Av, int K, const long long *__restrict__ vis_idx, const float *__restrict__ feat,
@@ -353,11 +365,7 @@ decode_backward_kernel(int Av, int K, int ntiles, const long long *__restrict__ 
 #pragma unroll
 						for (int c = 0; c < 7; c++) {
 							Z2[tid * ZS + 7 * k + c] = dz[c];
-							if (dz[c] != 0.f) {
-								const float *wr = s.w2[1] + (7 * k + c) * DEC_HID;
-#pragma unroll
-								for (int j = 0; j < DEC_HID; j++) dh[j] = fmaf(wr[j], dz[c], dh[j]);
-							}
+							if (dz[c] != 0.f) decode_axpy<DEC_HID>(s.w2[1] + (7 * k + c) * DEC_HID, dz[c], dh);
 						}
 					} else {
 						float dz = 0.f;
@@ -373,11 +381,7 @@ decode_backward_kernel(int Av, int K, int ntiles, const long long *__restrict__ 
 							}
 						}
 						Z2[tid * ZS + k] = dz;
-						if (dz != 0.f) {
-							const float *wr = s.w2[m] + k * DEC_HID;
-#pragma unroll
-							for (int j = 0; j < DEC_HID; j++) dh[j] = fmaf(wr[j], dz, dh[j]);
-						}
+						if (dz != 0.f) decode_axpy<DEC_HID>(s.w2[m] + k * DEC_HID, dz, dh);
 					}
 					r += sv;
 				}
@@ -386,30 +390,44 @@ decode_backward_kernel(int Av, int K, int ntiles, const long long *__restrict__ 
 					const float d1 = h[j] > 0.f ? dh[j] : 0.f; // ReLU
 					H[tid * DBW_HS + j] = h[j];
 					Z1[tid * DBW_HS + j] = d1;
-					if (d1 != 0.f) {
-						const float *wr = s.w1[m] + j * DEC_IN;
-#pragma unroll
-						for (int i = 0; i < DEC_IN; i++) dx[i] = fmaf(wr[i], d1, dx[i]);
-					}
+					if (d1 != 0.f) decode_axpy<DEC_IN>(s.w1[m] + j * DEC_IN, d1, dx);
 				}
 			}
 			__syncthreads();
 			// ---- phase B: weight gradients of this MLP over the tile ----
 			{
 				float *gW1 = sdW + (s.w1[m] - dsm), *gb1 = sdW + (s.b1[m] - dsm), *gW2 = sdW + (s.w2[m] - dsm), *gb2 = sdW + (s.b2[m] - dsm);
-				for (int o = tid; o < DEC_HID * DEC_IN; o += DBW_NT) {
-					const int j = o / DEC_IN, i = o - j * DEC_IN;
-					float acc = 0.f;
-#pragma unroll 8
-					for (int n = 0; n < DEC_NT; n++) acc = fmaf(Z1[n * DBW_HS + j], X[n * DBW_XS + i], acc);
-					gW1[o] += acc;
-				}
-				for (int o = tid; o < outs[m] * DEC_HID; o += DBW_NT) {
-					const int o2 = o / DEC_HID, j = o - o2 * DEC_HID;
-					float acc = 0.f;
-#pragma unroll 8
-					for (int n = 0; n < DEC_NT; n++) acc = fmaf(Z2[n * ZS + o2], H[n * DBW_HS + j], acc);
-					gW2[o] += acc;
+				// 4 x 4 register tiles: 8 shared-memory reads per 16 FMAs.  dW1 has 8 x 9 tiles, dW2 ceil(outs / 4) x 8.
+				const int t1 = (DEC_HID / 4) * (DEC_IN / 4), t2 = ((outs[m] + 3) / 4) * (DEC_HID / 4);
+				for (int tb = tid; tb < t1 + t2; tb += DBW_NT) {
+					const bool first = tb < t1;
+					const int tt = first ? tb : tb - t1;
+					const int cols = first ? DEC_IN / 4 : DEC_HID / 4;
+					const int r0 = 4 * (tt / cols), c0 = 4 * (tt % cols);
+					const float *Ap = first ? Z1 : Z2, *Bp = first ? X : H;
+					const int as = first ? DBW_HS : ZS, bs = first ? DBW_XS : DBW_HS;
+					const int rmax = first ? DEC_HID : outs[m];
+					float acc[4][4] = {};
+					int ra[4];
+#pragma unroll
+					for (int r = 0; r < 4; r++) ra[r] = min(r0 + r, rmax - 1); // clamp the ragged last tile (results discarded)
+#pragma unroll 4
+					for (int n = 0; n < DEC_NT; n++) {
+						float av[4], bv[4];
+#pragma unroll
+						for (int r = 0; r < 4; r++) { av[r] = Ap[n * as + ra[r]]; bv[r] = Bp[n * bs + c0 + r]; }
+#pragma unroll
+						for (int r = 0; r < 4; r++)
+#pragma unroll
+							for (int c = 0; c < 4; c++) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+					}
+					float *G = first ? gW1 : gW2;
+					const int gs = first ? DEC_IN : DEC_HID;
+#pragma unroll
+					for (int r = 0; r < 4; r++)
+						if (r0 + r < rmax)
+#pragma unroll
+							for (int c = 0; c < 4; c++) G[(r0 + r) * gs + c0 + c] += acc[r][c];
 				}
 				if (tid < DEC_HID) {
 					float acc = 0.f;
