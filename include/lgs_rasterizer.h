@@ -228,6 +228,22 @@ int lgs_decode_backward(int Av, int K, const long long *vis_idx, const float *fe
                         float *d_feat, float *d_anchor, float *d_offset, float *d_scaling, float *dW,
                         void *stream);
 
+/* ==== image-space training losses (the step right after the rasterizer) ==============
+ * Fused replacement of train.py:151-203 + utils/loss_utils.py:18-64 for color_channel = 2: image [2,H,W] (intensity,
+ * ray-drop), depth [1,H,W], gt_image [3,H,W] (ray-drop mask, intensity, depth).  `window` = the 121 floats of the
+ * reference's 11x11 Gaussian window (loss_utils.py:28-32).
+ *   lgs_loss_forward : sums[5] (double, zeroed here) = sum |x - gt| (intensity), sum |d - gt| (depth),
+ *                      sum (raydrop - mask)^2, sum of the SSIM map, sum of the masked depth-gradient L1;
+ *                      maps [3,H,W] = the per-pixel SSIM factors the backward needs
+ *   lgs_loss_backward: d_image [2,H,W], d_depth [1,H,W] = gradient of
+ *                      depth_loss + (1 - lambda) Ll1 + lambda (1 - SSIM) + 10 MSE(raydrop) + grad_loss
+ */
+int lgs_loss_forward(int H, int W, const float *image, const float *depth, const float *gt_image,
+                     const float *window, float *maps, double *sums, void *stream);
+int lgs_loss_backward(int H, int W, const float *image, const float *depth, const float *gt_image,
+                      const float *window, const float *maps, float lambda_dssim,
+                      float *d_image, float *d_depth, void *stream);
+
 /* ---- knobs and introspection (no reference counterpart) -------------------------------- */
 
 /* Rows of 16x1 tiles that share one depth-binned list (1, 2, 4, 8 or 16; 0 = auto). */
