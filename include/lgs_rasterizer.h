@@ -234,12 +234,15 @@ int lgs_decode_backward(int Av, int K, const long long *vis_idx, const float *fe
  * reference's 11x11 Gaussian window (loss_utils.py:28-32).
  *   lgs_loss_forward : sums[5] (double, zeroed here) = sum |x - gt| (intensity), sum |d - gt| (depth),
  *                      sum (raydrop - mask)^2, sum of the SSIM map, sum of the masked depth-gradient L1;
- *                      maps [3,H,W] = the per-pixel SSIM factors the backward needs
+ *                      maps [3,H,W] = the per-pixel SSIM factors the backward needs;
+ *                      values[6] = Ll1, depth_loss, ssim_loss (= 1 - mean SSIM), raydrop_loss, grad_loss and their
+ *                      weighted total (the line below)
  *   lgs_loss_backward: d_image [2,H,W], d_depth [1,H,W] = gradient of
  *                      depth_loss + (1 - lambda) Ll1 + lambda (1 - SSIM) + 10 MSE(raydrop) + grad_loss
  */
 int lgs_loss_forward(int H, int W, const float *image, const float *depth, const float *gt_image,
-                     const float *window, float *maps, double *sums, void *stream);
+                     const float *window, float lambda_dssim, float *maps, double *sums, float *values,
+                     void *stream);
 int lgs_loss_backward(int H, int W, const float *image, const float *depth, const float *gt_image,
                       const float *window, const float *maps, float lambda_dssim,
                       float *d_image, float *d_depth, void *stream);

@@ -94,6 +94,16 @@ loss_fwd_kernel(int H, int W, const float *__restrict__ image, const float *__re
 	}
 }
 
+// sums -> the five loss values and their weighted total (train.py:164-203), so that the host side needs no scalar kernels
+__global__ void loss_finalize_kernel(int H, int W, float lambda_dssim, const double *__restrict__ sums, float *__restrict__ out)
+{
+	const double n = (double)H * (double)W;
+	const double Ll1 = sums[0] / n, depth_loss = sums[1] / n, raydrop = 10.0 * sums[2] / n, ssim_loss = 1.0 - sums[3] / n;
+	const double grad_loss = sums[4] / ((double)H * (double)(W - 1));
+	out[0] = (float)Ll1; out[1] = (float)depth_loss; out[2] = (float)ssim_loss; out[3] = (float)raydrop; out[4] = (float)grad_loss;
+	out[5] = (float)(depth_loss + (1.0 - lambda_dssim) * Ll1 + lambda_dssim * ssim_loss + raydrop + grad_loss);
+}
+
 __global__ void __launch_bounds__(LTH * LTW)
 loss_bwd_kernel(int H, int W, const float *__restrict__ image, const float *__restrict__ depth, const float *__restrict__ gt,
 		const float *__restrict__ window, const float *__restrict__ maps, float lambda_dssim, float *__restrict__ d_image,
@@ -152,13 +162,14 @@ loss_bwd_kernel(int H, int W, const float *__restrict__ image, const float *__re
 extern "C" {
 
 int lgs_loss_forward(int H, int W, const float *image, const float *depth, const float *gt_image, const float *window,
-		     float *maps, double *sums, void *stream)
+		     float lambda_dssim, float *maps, double *sums, float *values, void *stream)
 {
-	if (H <= 0 || W <= 1 || !image || !depth || !gt_image || !window || !maps || !sums) return LGS_EINVAL;
+	if (H <= 0 || W <= 1 || !image || !depth || !gt_image || !window || !maps || !sums || !values) return LGS_EINVAL;
 	cudaStream_t st = (cudaStream_t)stream;
 	if (cudaMemsetAsync(sums, 0, 5 * sizeof(double), st) != cudaSuccess) return LGS_ECUDA;
 	dim3 grid((W + LTW - 1) / LTW, (H + LTH - 1) / LTH);
 	loss_fwd_kernel<<<grid, LTH * LTW, 0, st>>>(H, W, image, depth, gt_image, window, maps, sums);
+	loss_finalize_kernel<<<1, 1, 0, st>>>(H, W, lambda_dssim, sums, values);
 	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;
 }
 

@@ -24,7 +24,7 @@ def _lib():
     if not _bound:
         vp, i = C.c_void_p, C.c_int
         L.lgs_loss_forward.restype = i
-        L.lgs_loss_forward.argtypes = [i, i, vp, vp, vp, vp, vp, vp, vp]
+        L.lgs_loss_forward.argtypes = [i, i, vp, vp, vp, vp, C.c_float, vp, vp, vp, vp]
         L.lgs_loss_backward.restype = i
         L.lgs_loss_backward.argtypes = [i, i, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp]
         _bound = True
@@ -53,20 +53,17 @@ class _LossFn(torch.autograd.Function):
         win = _window(dev)
         maps = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         sums = torch.empty(5, dtype=torch.float64, device=dev)
+        values = torch.empty(6, dtype=torch.float32, device=dev)
         p = lambda t: C.c_void_p(t.data_ptr())
         st = torch.cuda.current_stream(dev).cuda_stream
-        if _lib().lgs_loss_forward(H, W, p(img), p(dep), p(gt), p(win), p(maps), p(sums), C.c_void_p(st)) < 0:
+        if _lib().lgs_loss_forward(H, W, p(img), p(dep), p(gt), p(win), float(lambda_dssim), p(maps), p(sums), p(values),
+                                   C.c_void_p(st)) < 0:
             raise capi.LgsError("lgs_loss_forward failed")
-        n = float(H * W)
-        Ll1, depth_loss = sums[0] / n, sums[1] / n
-        raydrop_loss, ssim_loss = 10.0 * sums[2] / n, 1.0 - sums[3] / n
-        grad_loss = sums[4] / float(H * (W - 1))
-        total = depth_loss + (1.0 - lambda_dssim) * Ll1 + lambda_dssim * ssim_loss + raydrop_loss + grad_loss
         ctx.save_for_backward(img, dep, gt, maps)
         ctx.lam = float(lambda_dssim)
-        parts = torch.stack([Ll1, depth_loss, ssim_loss, raydrop_loss, grad_loss]).float()
+        parts = values[:5]
         ctx.mark_non_differentiable(parts)
-        return total.float(), parts
+        return values[5], parts
 
     @staticmethod
     def backward(ctx, g_total, _g_parts):
