@@ -247,6 +247,19 @@ int lgs_loss_backward(int H, int W, const float *image, const float *depth, cons
                       const float *window, const float *maps, float lambda_dssim,
                       float *d_image, float *d_depth, void *stream);
 
+/* ==== densification statistics (the consumer of means2D.grad) =========================
+ * Fused replacement of scene/gaussian_model.py:597-618 GaussianModel.training_statis.  anchor_visible [A] and
+ * selection_mask [Av*K] / update_filter [M] are byte masks; vis_rank [A] / sel_rank [Av*K] are the INCLUSIVE int32
+ * prefix sums of anchor_visible / selection_mask (they turn masks into row numbers); opacity [Av*K] is the decode's
+ * neural_opacity; means2D_grad [M,4] the gradient of the rasterizer's screen-space holder.  Accumulators are updated
+ * in place: opacity_accum [A], anchor_demon [A], offset_gradient_accum [A*K], offset_denom [A*K].
+ */
+int lgs_training_statis(int A, int K, const unsigned char *anchor_visible, const int *vis_rank,
+                        const float *opacity, const unsigned char *selection_mask, const int *sel_rank,
+                        const unsigned char *update_filter, const float *means2D_grad,
+                        float *opacity_accum, float *anchor_demon, float *offset_gradient_accum,
+                        float *offset_denom, void *stream);
+
 /* ---- knobs and introspection (no reference counterpart) -------------------------------- */
 
 /* Rows of 16x1 tiles that share one depth-binned list (1, 2, 4, 8 or 16; 0 = auto). */

@@ -98,3 +98,53 @@ int lgs_grad_scatter_add(int P, const float *gathered, int nranks, int my_rank, 
 }
 
 } // extern "C"
+
+// ---- densification statistics (the consumer of means2D.grad) --------------------------------------
+// Restates scene/gaussian_model.py:597-618 training_statis: per visible anchor, accumulate the clamped neural opacities
+// and the visit count; per rendered neural Gaussian (selected by the opacity mask AND visible in the frame, radii > 0),
+// accumulate the norm of the last two columns of the screen-space gradient holder (the rasterizer's densification
+// statistic, R3 backward.cu:779) and a counter.  The reference does this with a dozen boolean-index scatter kernels and
+// three [A*K] temporaries; here one thread per anchor, given the two prefix sums that turn masks into row numbers.
+namespace {
+__global__ void __launch_bounds__(256)
+training_statis_kernel(int A, int K, const unsigned char *__restrict__ anchor_visible, const int *__restrict__ vis_rank,
+		       const float *__restrict__ opacity, const unsigned char *__restrict__ sel, const int *__restrict__ sel_rank,
+		       const unsigned char *__restrict__ update_filter, const float *__restrict__ grad4, float *__restrict__ opacity_accum,
+		       float *__restrict__ anchor_demon, float *__restrict__ offset_gradient_accum, float *__restrict__ offset_denom)
+{
+	const int a = blockIdx.x * blockDim.x + threadIdx.x;
+	if (a >= A || !anchor_visible[a]) return;
+	const size_t v = (size_t)vis_rank[a] - 1; // inclusive prefix sum of the visibility mask -> rank among the visible anchors
+	float acc = 0.f;
+	for (int k = 0; k < K; k++) {
+		const size_t i = v * K + k;
+		acc += fmaxf(opacity[i], 0.f);                         // :599-603
+		if (sel[i]) {
+			const size_t r = (size_t)sel_rank[i] - 1;          // row of this offset among the decoded Gaussians
+			if (update_filter[r]) {                            // :608-618
+				const float gx = grad4[4 * r + 2], gy = grad4[4 * r + 3];
+				offset_gradient_accum[(size_t)a * K + k] += sqrtf(gx * gx + gy * gy);
+				offset_denom[(size_t)a * K + k] += 1.f;
+			}
+		}
+	}
+	opacity_accum[a] += acc;
+	anchor_demon[a] += 1.f;                                        // :606
+}
+} // namespace
+
+extern "C" int lgs_training_statis(int A, int K, const unsigned char *anchor_visible, const int *vis_rank, const float *opacity,
+				   const unsigned char *selection_mask, const int *sel_rank, const unsigned char *update_filter,
+				   const float *means2D_grad, float *opacity_accum, float *anchor_demon, float *offset_gradient_accum,
+				   float *offset_denom, void *stream)
+{
+	if (A < 0 || K < 1) return LGS_EINVAL;
+	if (A == 0) return 0;
+	if (!anchor_visible || !vis_rank || !opacity || !selection_mask || !sel_rank || !update_filter || !means2D_grad || !opacity_accum ||
+	    !anchor_demon || !offset_gradient_accum || !offset_denom)
+		return LGS_EINVAL;
+	training_statis_kernel<<<(A + 255) / 256, 256, 0, (cudaStream_t)stream>>>(A, K, anchor_visible, vis_rank, opacity, selection_mask,
+										    sel_rank, update_filter, means2D_grad, opacity_accum,
+										    anchor_demon, offset_gradient_accum, offset_denom);
+	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;
+}
