@@ -171,13 +171,18 @@ int lgs_surfel_mark_visible(int P, const float *means3D, const float *viewmatrix
  * A frame's backward leaves most Gaussians untouched (zero gradient), so instead of a dense all-reduce of the
  * 13 P-float gradient bucket the ranks can all-gather only their touched rows (lgs_b200/dp.py SparseExchange):
  *   lgs_backward_touched : device pointers to the id list / count lgs_backward() left in its scratch
- *   lgs_grad_pack        : (cap + 1) rows of 64 bytes: row 0 = {count, cap}, row i + 1 = {id, dmean3D 3, dscale 3,
- *                          dopacity, drot 4, dcolor 2, pad 2} of the i-th touched Gaussian
+ *   lgs_grad_count       : *nonzero (device) = touched Gaussians whose 13 gradient floats are not all zero
+ *   lgs_grad_pack        : (cap + 1) rows of 64 bytes: row 0 = {number of rows}, rows 1.. = {id, dmean3D 3, dscale 3,
+ *                          dopacity, drot 4, dcolor 2, pad 2} of the touched Gaussians with a non-zero gradient
+ *                          (any order); cap must be >= lgs_grad_count()'s result
  *   lgs_grad_scatter_add : adds the rows of every OTHER rank (gathered = nranks packed buffers back to back) into
  *                          the local dense gradient arrays -> the same sums a dense all-reduce gives
  */
 int lgs_backward_touched(float *grad_scratch, int P, const uint32_t **ids, const uint32_t **count);
 size_t lgs_grad_pack_bytes(int cap);
+int lgs_grad_count(const uint32_t *ids, const uint32_t *count,
+                   const float *dL_dmean3D, const float *dL_dscale, const float *dL_drot,
+                   const float *dL_dopacity, const float *dL_dcolor, unsigned *nonzero, void *stream);
 int lgs_grad_pack(const uint32_t *ids, const uint32_t *count, int cap,
                   const float *dL_dmean3D, const float *dL_dscale, const float *dL_drot,
                   const float *dL_dopacity, const float *dL_dcolor, float *packed, void *stream);

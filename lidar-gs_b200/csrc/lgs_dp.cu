@@ -12,19 +12,48 @@
 
 namespace {
 
+// The touched list holds every Gaussian in a replayed list prefix; only a fraction of them ends up with a non-zero
+// gradient (cfg3: 33 k of 160 k).  Rows that are entirely zero are not worth sending.
+__device__ __forceinline__ bool grad_row_nonzero(unsigned id, const float *__restrict__ d_means3D, const float *__restrict__ d_scales,
+						 const float *__restrict__ d_rot, const float *__restrict__ d_opac,
+						 const float *__restrict__ d_colors)
+{
+	const float *m = d_means3D + 3 * (size_t)id, *s = d_scales + 3 * (size_t)id, *c = d_colors + 2 * (size_t)id;
+	const float4 r = *reinterpret_cast<const float4 *>(d_rot + 4 * (size_t)id);
+	return m[0] != 0.f || m[1] != 0.f || m[2] != 0.f || s[0] != 0.f || s[1] != 0.f || s[2] != 0.f || d_opac[id] != 0.f || r.x != 0.f ||
+	       r.y != 0.f || r.z != 0.f || r.w != 0.f || c[0] != 0.f || c[1] != 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+grad_count_kernel(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ count, const float *__restrict__ d_means3D,
+		  const float *__restrict__ d_scales, const float *__restrict__ d_rot, const float *__restrict__ d_opac,
+		  const float *__restrict__ d_colors, unsigned *__restrict__ nonzero)
+{
+	const unsigned n = *count;
+	unsigned c = 0;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+		c += grad_row_nonzero(ids[i], d_means3D, d_scales, d_rot, d_opac, d_colors);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+	if ((threadIdx.x & 31) == 0 && c) atomicAdd(nonzero, c);
+}
+
+// packed[0] (the header) must be zero on entry: its first word is the row counter
 __global__ void __launch_bounds__(256)
 grad_pack_kernel(const uint32_t *__restrict__ ids, const uint32_t *__restrict__ count, int cap, const float *__restrict__ d_means3D,
 		 const float *__restrict__ d_scales, const float *__restrict__ d_rot, const float *__restrict__ d_opac,
 		 const float *__restrict__ d_colors, float4 *__restrict__ packed)
 {
-	const unsigned n = min(*count, (unsigned)cap);
-	if (blockIdx.x == 0 && threadIdx.x == 0)
-		packed[0] = make_float4(__uint_as_float(*count), __uint_as_float((unsigned)cap), 0.f, 0.f);
+	const unsigned n = *count;
+	unsigned *counter = reinterpret_cast<unsigned *>(packed);
 	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const unsigned id = ids[i];
+		if (!grad_row_nonzero(id, d_means3D, d_scales, d_rot, d_opac, d_colors)) continue;
+		const unsigned slot = atomicAdd(counter, 1u);
+		if (slot >= (unsigned)cap) continue; // cannot happen when cap >= lgs_grad_count()'s result
 		const float *m = d_means3D + 3 * (size_t)id, *s = d_scales + 3 * (size_t)id, *c = d_colors + 2 * (size_t)id;
 		const float4 r = *reinterpret_cast<const float4 *>(d_rot + 4 * (size_t)id);
-		float4 *row = packed + 4 * ((size_t)i + 1);
+		float4 *row = packed + 4 * ((size_t)slot + 1);
 		row[0] = make_float4(__uint_as_float(id), m[0], m[1], m[2]);
 		row[1] = make_float4(s[0], s[1], s[2], d_opac[id]);
 		row[2] = r;
@@ -74,11 +103,22 @@ int lgs_backward_touched(float *grad_scratch, int P, const uint32_t **ids, const
 
 size_t lgs_grad_pack_bytes(int cap) { return ((size_t)(cap > 0 ? cap : 0) + 1) * 64; }
 
+int lgs_grad_count(const uint32_t *ids, const uint32_t *count, const float *dL_dmean3D, const float *dL_dscale, const float *dL_drot,
+		   const float *dL_dopacity, const float *dL_dcolor, unsigned *nonzero, void *stream)
+{
+	if (!ids || !count || !dL_dmean3D || !dL_dscale || !dL_drot || !dL_dopacity || !dL_dcolor || !nonzero) return LGS_EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (cudaMemsetAsync(nonzero, 0, sizeof(unsigned), st) != cudaSuccess) return LGS_ECUDA;
+	grad_count_kernel<<<148 * 4, 256, 0, st>>>(ids, count, dL_dmean3D, dL_dscale, dL_drot, dL_dopacity, dL_dcolor, nonzero);
+	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;
+}
+
 int lgs_grad_pack(const uint32_t *ids, const uint32_t *count, int cap, const float *dL_dmean3D, const float *dL_dscale,
 		  const float *dL_drot, const float *dL_dopacity, const float *dL_dcolor, float *packed, void *stream)
 {
 	if (!ids || !count || cap < 0 || !dL_dmean3D || !dL_dscale || !dL_drot || !dL_dopacity || !dL_dcolor || !packed) return LGS_EINVAL;
-	const int blocks = max(1, min((cap + 255) / 256, 148 * 4));
+	if (cudaMemsetAsync(packed, 0, 16, (cudaStream_t)stream) != cudaSuccess) return LGS_ECUDA; // header: row counter
+	const int blocks = 148 * 4;
 	grad_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ids, count, cap, dL_dmean3D, dL_dscale, dL_drot, dL_dopacity, dL_dcolor,
 								    (float4 *)packed);
 	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;

@@ -126,6 +126,17 @@ class SparseExchange:
             raise self.capi.LgsError("lgs_backward_touched failed")
         return ids.value, cnt.value
 
+    def count_nonzero(self, ids_ptr, cnt_ptr, views, stream=None):
+        """-> self._cnt (1-element int32 device tensor): touched Gaussians whose gradient row is not all zero."""
+        import ctypes as C
+        st = torch.cuda.current_stream(self.dev).cuda_stream if stream is None else stream
+        p = lambda t: C.c_void_p(t.data_ptr())
+        rc = self.L.lgs_grad_count(C.c_void_p(ids_ptr), C.c_void_p(cnt_ptr), p(views["means3D"]), p(views["scales"]),
+                                   p(views["rotations"]), p(views["opacities"]), p(views["colors"]), p(self._cnt), C.c_void_p(st))
+        if rc < 0:
+            raise self.capi.LgsError("lgs_grad_count failed")
+        return self._cnt
+
     def pack(self, ids_ptr, cnt_ptr, cap, views, stream=None):
         import ctypes as C
         n = self.L.lgs_grad_pack_bytes(cap) // 4
@@ -155,8 +166,8 @@ class SparseExchange:
         if self.world == 1:
             return
         ids_ptr, cnt_ptr = self.touched(grad_scratch)
-        # count -> max over ranks -> host (sizes the gather)
-        self._cnt.copy_(_device_u32(cnt_ptr, self.dev))
+        # rows worth sending (non-zero gradient) -> max over ranks -> host (sizes the gather)
+        self.count_nonzero(ids_ptr, cnt_ptr, views)
         dist.all_reduce(self._cnt, op=dist.ReduceOp.MAX, group=self.group)
         cap = int(self._cnt.item())
         cap = (cap + 1023) // 1024 * 1024

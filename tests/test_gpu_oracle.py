@@ -198,7 +198,9 @@ def test_sparse_gradient_exchange_equals_dense_sum():
         listed[ids] = True
         assert bool((listed | ~nz_g).all()) and ids.unique().numel() == cnt
         buckets.append((b, grads))
-        caps.append(cnt)
+        nzc = int(xs.count_nonzero(ids_ptr, cnt_ptr, views_of(b)).item())
+        assert nzc == int(nz_g.sum().item()) and nzc <= cnt  # only rows with a gradient are sent
+        caps.append(nzc)
     cap = (max(caps) + 1023) // 1024 * 1024
     for (b, grads) in buckets:
         ids_ptr, cnt_ptr = xs.touched(grads["scratch"])
