@@ -265,6 +265,38 @@ int lgs_training_statis(int A, int K, const unsigned char *anchor_visible, const
                         float *opacity_accum, float *anchor_demon, float *offset_gradient_accum,
                         float *offset_denom, void *stream);
 
+/* ==== evaluation metrics =========================================================
+ * lgs_chamfer_forward   replaces extern/chamfer3D/chamfer3D.cu:143-166 chamfer_cuda_forward (NmDistanceKernel :9-141,
+ *                       twice): for every point of xyz1 [b,n,3] the squared distance to / index of its nearest point
+ *                       in xyz2 [b,m,3] (dist1, idx1 [b,n]) and vice versa (dist2, idx2 [b,m]).  Bit-identical to the
+ *                       reference for finite inputs (same fp32 evaluation order, ties to the smallest index); with an
+ *                       empty target cloud the outputs are zeros, as the reference leaves them.  `scratch`:
+ *                       lgs_chamfer_scratch_bytes() device bytes.  `stats` (device, may be NULL): 3 counters that are
+ *                       ADDED to -- 64-target sub-tiles evaluated by a warp, warp x sub-tile pairs, 256-target tiles loaded by a CTA.
+ * lgs_chamfer_backward  replaces chamfer3D.cu:196-227 chamfer_cuda_backward: grad_xyz1 / grad_xyz2 (ACCUMULATED
+ *                       into, like the reference's atomicAdd on caller-zeroed tensors).
+ * lgs_pano_to_lidar     replaces utils/lidar_utils.py:171-231 pano_to_lidar(_with_intensities) (numpy on the host in
+ *                       the reference): points [count, stride] (stride 3: xyz, 4: xyz + intensity) of the non-zero
+ *                       range-image pixels in row-major order; beam_inclinations [H] ascending as
+ *                       get_beam_inclinations returns them (NULL: the fov_up / fov formula, degrees); `points` must
+ *                       hold H*W rows; *count (device int) = rows written; scratch: lgs_pano_scratch_bytes(H).
+ * lgs_chamfer_fscore    replaces utils/lidar_utils.py:272-275 + extern/fscore.py:4-18: out[4*i..] = { mean(dist1) +
+ *                       mean(dist2), F-score, precision_1, precision_2 } of batch item i at `threshold`.
+ */
+size_t lgs_chamfer_scratch_bytes(int b, int n, int m);
+int lgs_chamfer_forward(int b, int n, const float *xyz1, int m, const float *xyz2,
+                        float *dist1, int *idx1, float *dist2, int *idx2,
+                        void *scratch, unsigned long long *stats, void *stream);
+int lgs_chamfer_backward(int b, int n, const float *xyz1, int m, const float *xyz2,
+                         const float *grad_dist1, const int *idx1, const float *grad_dist2, const int *idx2,
+                         float *grad_xyz1, float *grad_xyz2, void *stream);
+size_t lgs_pano_scratch_bytes(int H);
+int lgs_pano_to_lidar(int H, int W, const float *pano, const float *intensities,
+                      const float *beam_inclinations, float fov_up, float fov, int stride,
+                      float *points, int *count, void *scratch, void *stream);
+int lgs_chamfer_fscore(int b, int n, const float *dist1, int m, const float *dist2, float threshold,
+                       float *out, void *stream);
+
 /* ---- knobs and introspection (no reference counterpart) -------------------------------- */
 
 /* Rows of 16x1 tiles that share one depth-binned list (1, 2, 4, 8 or 16; 0 = auto). */

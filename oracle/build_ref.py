@@ -44,13 +44,27 @@ def build_surfel(force=False):
     return _build(RS, NAME_SURFEL, force, ["-include", NOPRINTF])
 
 
-def _build(R3, NAME, force, kernel_flags):
+CH = os.path.join(REF, "extern", "chamfer3D")
+NAME_CHAMFER = "chamfer_ref_3D"
+
+
+def build_chamfer(force=False):
+    """oracle/_ref/chamfer_ref_3D.so from extern/chamfer3D (chamfer3D.cu + chamfer_cuda.cpp, the list in its setup.py):
+    the reference's nearest-neighbour distance extension, used by its eval metrics (utils/lidar_utils.py:256-279)."""
+    return _build(CH, NAME_CHAMFER, force, [], srcs=["chamfer3D.cu", "chamfer_cuda.cpp"])
+
+
+def load_chamfer():
+    return load(NAME_CHAMFER)
+
+
+def _build(R3, NAME, force, kernel_flags, srcs=None):
     so = os.path.join(OUT, NAME + ".so")
     if not os.path.isdir(R3):
         # GPU box / fresh clone: nothing to build from; use the prebuilt file if present
         return so if os.path.exists(so) else None
-    srcs = ["cuda_rasterizer/rasterizer_impl.cu", "cuda_rasterizer/forward.cu",
-            "cuda_rasterizer/backward.cu", "rasterize_points.cu", "ext.cpp"]
+    srcs = srcs or ["cuda_rasterizer/rasterizer_impl.cu", "cuda_rasterizer/forward.cu",
+                    "cuda_rasterizer/backward.cu", "rasterize_points.cu", "ext.cpp"]
     srcs = [os.path.join(R3, s) for s in srcs]
     if os.path.exists(so) and not force:
         if all(os.path.getmtime(so) > os.path.getmtime(s) for s in srcs):
@@ -113,3 +127,4 @@ def load(NAME=NAME):
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
     print(build_surfel(force="--force" in sys.argv))
+    print(build_chamfer(force="--force" in sys.argv))
