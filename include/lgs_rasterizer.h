@@ -297,6 +297,27 @@ int lgs_pano_to_lidar(int H, int W, const float *pano, const float *intensities,
 int lgs_chamfer_fscore(int b, int n, const float *dist1, int m, const float *dist2, float threshold,
                        float *out, void *stream);
 
+/* ==== optimizer step (the other half) ==============================================
+ * lgs_adam_step: the Adam update of every parameter tensor in ONE launch (per LGS_ADAM_MAX_TENSORS tensors), replacing
+ * what `self.optimizer.step()` (train.py:243, optimizer built at scene/gaussian_model.py:390 as
+ * torch.optim.Adam(l, lr=0.0, eps=1e-15)) runs on CUDA: torch's foreach Adam, seven multi-tensor launches per step.
+ * amsgrad = False, weight_decay = 0, maximize = False only (what the reference uses).  Per tensor the caller passes the
+ * scalars torch/optim/adam.py:773-781 derives in double from (lr, betas, eps, step), rounded to float:
+ *   lerp_weight = 1 - beta1, beta2, one_minus_beta2 = 1 - beta2, eps,
+ *   step_size = -lr / (1 - beta1^step), bias_correction2_sqrt = sqrt(1 - beta2^step)
+ * param, exp_avg, exp_avg_sq are updated in place, bit-identical to torch.optim.Adam's foreach path.
+ */
+#define LGS_ADAM_MAX_TENSORS 48
+typedef struct lgs_adam_tensor {
+	float *param;
+	const float *grad;
+	float *exp_avg;
+	float *exp_avg_sq;
+	long long numel;
+	float lerp_weight, beta2, one_minus_beta2, eps, step_size, bias_correction2_sqrt;
+} lgs_adam_tensor;
+int lgs_adam_step(int ntensors, const lgs_adam_tensor *tensors, void *stream);
+
 /* ---- knobs and introspection (no reference counterpart) -------------------------------- */
 
 /* Rows of 16x1 tiles that share one depth-binned list (1, 2, 4, 8 or 16; 0 = auto). */
