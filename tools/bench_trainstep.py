@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 
 import diff_lidargs_rasterization as dlr
-from lgs_b200 import losses, neural_gaussians as ng, statistics, synth
+from lgs_b200 import losses, neural_gaussians as ng, optim, statistics, synth
 
 A, K, H, W = 333333, 6, 64, 2048
 dev = torch.device("cuda:0")
@@ -80,7 +80,13 @@ def eager_losses(img, dep, lam=0.2):
             + (pg * m - gg * m).abs().mean())
 
 
-def iteration(fused):
+# the reference's optimizer (scene/gaussian_model.py:390), learning rates 0 so that every timed iteration sees the same parameters
+# (the update arithmetic runs in full; only its step size is zero)
+groups = lambda: [dict(params=[p], lr=0.0, name=str(i)) for i, p in enumerate(params)]
+opt_fused, opt_torch = optim.Adam(groups(), lr=0.0, eps=1e-15), torch.optim.Adam(groups(), lr=0.0, eps=1e-15)
+
+
+def iteration(fused, with_optimizer=False):
     for p in params:
         p.grad = None
     scaling_act = torch.exp(log_scaling)
@@ -100,17 +106,19 @@ def iteration(fused):
     loss.backward()
     if fused:
         statistics.training_statis(PC, m2d, nop, radii > 0, mask, vis)
+    if with_optimizer:
+        (opt_fused if fused else opt_torch).step()
     return loss.detach(), xyz.shape[0]
 
 
-def timeit(fused, n=10):
+def timeit(fused, n=10, with_optimizer=False):
     for _ in range(3):
-        iteration(fused)
+        iteration(fused, with_optimizer)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n):
-        iteration(fused)
+        iteration(fused, with_optimizer)
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
@@ -124,4 +132,7 @@ line = dict(op="full training iteration (filter + decode + rasterizer fwd/bwd + 
             H=H, W=W, ms_fused=timeit(True), ms_eager_decode_and_losses=timeit(False), loss_fused=float(lf), loss_eager=float(le),
             rel_err_d_feat=float((gf - ge).abs().max() / ge.abs().max()))
 line["speedup"] = line["ms_eager_decode_and_losses"] / line["ms_fused"]
+line["ms_fused_with_adam"] = timeit(True, with_optimizer=True)            # + lgs_b200.optim.Adam.step(), one launch
+line["ms_eager_with_torch_adam"] = timeit(False, with_optimizer=True)     # + torch.optim.Adam.step(), foreach path
+line["speedup_with_optimizer"] = line["ms_eager_with_torch_adam"] / line["ms_fused_with_adam"]
 print(json.dumps(line))
