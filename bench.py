@@ -417,6 +417,8 @@ def main():
     ap.add_argument("--dense-allreduce", action="store_true",
                     help="N > 1: all-reduce the dense 13P-float bucket instead of all-gathering the touched rows")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-dense-grads", action="store_true",
+                    help="end-to-end leg copies the dense gradient arrays to the host instead of the non-zero rows")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--pose-rank", type=int, default=None, help="debug: render the frame rank K would render")
     args = ap.parse_args()
@@ -434,7 +436,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from lgs_b200 import capi, synth
+    from lgs_b200 import capi, dp, synth
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU baseline)")
     dev = torch.device(f"cuda:{local}")
@@ -466,7 +468,6 @@ def main():
     fr = capi.Frame(dev)
     xchg = None
     if world > 1 and not args.dense_allreduce:
-        from lgs_b200 import dp
         xchg = dp.SparseExchange(P, dev)
 
     def render():
@@ -530,13 +531,57 @@ def main():
         h_in = {k: pin(sc[k]) for k in ("means3D", "scales", "rotations", "opacities", "colors")}
         h_anc = dict(means=pin(anc["means"]), scales6=pin(anc["scales6"]), rots=pin(anc["rots"]))
         h_out = dict(color=torch.empty((2, H, W)).pin_memory(), depth=torch.empty((1, H, W)).pin_memory(),
-                     occ=torch.empty((1, H, W)).pin_memory(), bucket=torch.empty(13 * P).pin_memory(),
-                     means2D=torch.empty((P, 4)).pin_memory(), anchor_radii=torch.empty(anc["means"].shape[0], dtype=torch.int32).pin_memory())
+                     occ=torch.empty((1, H, W)).pin_memory(),
+                     anchor_radii=torch.empty(anc["means"].shape[0], dtype=torch.int32).pin_memory())
+        GRAD_KEYS = ("means3D", "scales", "rotations", "opacities", "colors")
+        GRAD_COLS = dict(means3D=3, scales=3, rotations=4, opacities=1, colors=2)
+        sparse_rows = not args.e2e_dense_grads
+        row_cap = 0
         settings = dlr.GaussianRasterizationSettings(
             image_height=H, image_width=W, tanfovx=1.0, tanfovy=1.0, bg=d["bg"], scale_modifier=1.0,
             viewmatrix=d["viewmatrix"], projmatrix=d["projmatrix"], sh_degree=1, campos=d["campos"], prefiltered=False,
             beam_inclinations=d["beams"], lidar_far=sc["far"], lidar_near=sc["near"], debug=False)
         rast = dlr.GaussianRasterizer(settings)
+
+        def frame_grads(b):
+            """forward + backward of one frame through the operator -> (images, anchor radii, dict of dense gradients [P, c])"""
+            g = {k: b[k].detach().requires_grad_(True) for k in h_in}
+            a_radii = rast.visible_filter(b["a_means"], b["a_scales6"][:, :3], b["a_rots"])
+            m2d = torch.zeros((P, 4), device=dev, requires_grad=True)
+            color, depth, occ, radii = rast(means3D=g["means3D"], means2D=m2d, shs=None, colors_precomp=g["colors"],
+                                            opacities=g["opacities"], scales=g["scales"], rotations=g["rotations"],
+                                            cov3D_precomp=None)
+            torch.autograd.backward([color, depth, occ], [d["g_color"], d["g_depth"], d["g_occ"]])
+            grads = {k: g[k].grad for k in GRAD_KEYS}
+            flat = None
+            if world > 1 or not sparse_rows:
+                flat = torch.cat([grads[k].reshape(-1) for k in GRAD_KEYS])
+                if world > 1:
+                    dist.all_reduce(flat)
+                    o = 0
+                    for k in GRAD_KEYS:
+                        grads[k] = flat[o:o + GRAD_COLS[k] * P].view(P, GRAD_COLS[k])
+                        o += GRAD_COLS[k] * P
+            return (color.detach(), depth.detach(), occ.detach()), a_radii, grads, m2d.grad, flat
+
+        if sparse_rows:
+            # The host gets every gradient row that is not zero (lossless: dp.unpack_rows() rebuilds the dense arrays) instead of
+            # the 17 P floats of the autograd surface.  Size the row buffer from one untimed frame and check the round trip.
+            b0 = {k: v.to(dev) for k, v in dict(h_in, a_means=h_anc["means"], a_scales6=h_anc["scales6"], a_rots=h_anc["rots"]).items()}
+            _, _, gr0, m2g0, _ = frame_grads(b0)
+            probe = dp.pack_nonzero_rows(gr0, m2g0, 0)
+            found0 = int(probe[0, :1].view(torch.int32).item())
+            row_cap = (int(found0 * 1.25) + 4096 + 4095) // 4096 * 4096
+            back, found = dp.unpack_rows(dp.pack_nonzero_rows(gr0, m2g0, row_cap).cpu().numpy(), P)
+            assert found == found0 <= row_cap
+            for k in GRAD_KEYS:
+                assert np.array_equal(back[k], gr0[k].cpu().numpy()), f"sparse read-back differs from the dense gradient: {k}"
+            assert np.array_equal(back["means2D"], m2g0.cpu().numpy())
+            h_out["grad_rows"] = torch.empty((row_cap + 1, dp.ROW_FLOATS)).pin_memory()
+            del b0, gr0, m2g0, probe, back
+        else:
+            h_out["bucket"] = torch.empty(13 * P).pin_memory()
+            h_out["means2D"] = torch.empty((P, 4)).pin_memory()
         h2d = sum(v.numel() * v.element_size() for v in h_in.values()) + sum(v.numel() * v.element_size() for v in h_anc.values())
         d2h = sum(v.numel() * v.element_size() for v in h_out.values())
 
@@ -573,16 +618,9 @@ def main():
                 ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ca.record(cur)
             b = d_bufs[i]
-            g = {k: b[k].detach().requires_grad_(True) for k in h_in}
-            a_radii = rast.visible_filter(b["a_means"], b["a_scales6"][:, :3], b["a_rots"])
-            m2d = torch.zeros((P, 4), device=dev, requires_grad=True)
-            color, depth, occ, radii = rast(means3D=g["means3D"], means2D=m2d, shs=None, colors_precomp=g["colors"],
-                                            opacities=g["opacities"], scales=g["scales"], rotations=g["rotations"],
-                                            cov3D_precomp=None)
-            torch.autograd.backward([color, depth, occ], [d["g_color"], d["g_depth"], d["g_occ"]])
-            flat = torch.cat([g[k].grad.reshape(-1) for k in ("means3D", "scales", "rotations", "opacities", "colors")])
-            if world > 1:
-                dist.all_reduce(flat)
+            (color, depth, occ), a_radii, grads, m2g, flat = frame_grads(b)
+            if sparse_rows:
+                rows = dp.pack_nonzero_rows(grads, m2g, row_cap)
             ev_free[i].record(cur)
             done = torch.cuda.Event()
             done.record(cur)
@@ -590,8 +628,11 @@ def main():
                 cb.record(cur)
                 dbg.append(("compute", ca, cb))
                 oa, ob = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            outs = dict(anchor_radii=a_radii, color=color.detach(), depth=depth.detach(), occ=occ.detach(), bucket=flat,
-                        means2D=m2d.grad)
+            outs = dict(anchor_radii=a_radii, color=color, depth=depth, occ=occ)
+            if sparse_rows:
+                outs["grad_rows"] = rows
+            else:
+                outs.update(bucket=flat, means2D=m2g)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(done)
                 if dbg is not None:
@@ -619,6 +660,9 @@ def main():
         e1.record()
         barrier()
         ms_e = e0.elapsed_time(e1)
+        if sparse_rows:  # no timed step may have found more rows than the buffer holds
+            worst = max(int(h["grad_rows"][0, :1].view(torch.int32).item()) for h in h_outs)
+            assert 0 < worst <= row_cap, f"sparse gradient read-back overflowed: {worst} rows > {row_cap}"
         if dbg:
             first = dbg[-3 * ke][1]
             for name, a_, b_ in dbg[-30:]:
@@ -630,7 +674,10 @@ def main():
         e2e = {"value": world * 1e3 / (ms_e / ke), "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": ke, "ms_per_step": ms_e / ke,
                "api": "diff_lidargs_rasterization.GaussianRasterizer (autograd) + visible_filter; H2D / compute / D2H on three "
-                      "streams, double buffered"}
+                      "streams, double buffered",
+               "results_read_back": ("images + anchor radii + every non-zero gradient row (80 B rows of lgs_grad_pack_nonzero, "
+                                     f"capacity {row_cap}; dp.unpack_rows() == the dense gradients, asserted before timing)")
+               if sparse_rows else "images + anchor radii + all dense gradients (17 P floats)"}
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:

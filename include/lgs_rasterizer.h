@@ -265,6 +265,17 @@ int lgs_training_statis(int A, int K, const unsigned char *anchor_visible, const
                         float *opacity_accum, float *anchor_demon, float *offset_gradient_accum,
                         float *offset_denom, void *stream);
 
+/* ---- sparse read-back of a frame's gradients (no reference counterpart; bench.py's end-to-end leg) ----------
+ * lgs_grad_pack_nonzero: one pass over the dense gradient arrays the backward wrote (dL_dmeans2D [P,4] may be NULL) that
+ * copies every Gaussian with a non-zero gradient into an 80-byte row {id, dmean3D 3, dscale 3, dopacity, drot 4, dcolor 2,
+ * dmeans2D 4, pad 2}, in any order.  packed: lgs_grad_rows_bytes(cap) device bytes; row 0 is a header whose first word
+ * counts the rows FOUND (rows beyond cap are dropped: found > cap tells the caller to fall back to the dense arrays).
+ */
+size_t lgs_grad_rows_bytes(int cap);
+int lgs_grad_pack_nonzero(int P, const float *dL_dmean3D, const float *dL_dscale, const float *dL_drot,
+                          const float *dL_dopacity, const float *dL_dcolor, const float *dL_dmeans2D,
+                          int cap, float *packed, void *stream);
+
 /* ==== evaluation metrics =========================================================
  * lgs_chamfer_forward   replaces extern/chamfer3D/chamfer3D.cu:143-166 chamfer_cuda_forward (NmDistanceKernel :9-141,
  *                       twice): for every point of xyz1 [b,n,3] the squared distance to / index of its nearest point

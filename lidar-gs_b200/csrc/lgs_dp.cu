@@ -139,6 +139,54 @@ int lgs_grad_scatter_add(int P, const float *gathered, int nranks, int my_rank, 
 
 } // extern "C"
 
+// ---- sparse read-back of a frame's gradients ---------------------------------------------------------------------------
+// A host-side consumer of the operator's gradients (a CPU optimizer, a parameter server, a logger) does not need the 17 P
+// floats the autograd surface returns, only the rows that are not zero: config 3 has 2 M Gaussians and ~45 k such rows.  One
+// pass over the dense arrays (HBM-bound, 68 B read per Gaussian) writes them as 80-byte rows
+// {id, dmean3D 3, dscale 3, dopacity, drot 4, dcolor 2, dmeans2D 4, pad 2}; the host copies (cap + 1) rows instead of 136 MB.
+namespace {
+__global__ void __launch_bounds__(256)
+grad_pack_nonzero_kernel(int P, const float *__restrict__ d_means3D, const float *__restrict__ d_scales, const float *__restrict__ d_rot,
+			 const float *__restrict__ d_opac, const float *__restrict__ d_colors, const float4 *__restrict__ d_means2D, int cap,
+			 float4 *__restrict__ packed)
+{
+	unsigned *counter = reinterpret_cast<unsigned *>(packed);
+	for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < P; id += gridDim.x * blockDim.x) {
+		const float *m = d_means3D + 3 * (size_t)id, *s = d_scales + 3 * (size_t)id, *c = d_colors + 2 * (size_t)id;
+		const float4 r = *reinterpret_cast<const float4 *>(d_rot + 4 * (size_t)id);
+		const float4 m2 = d_means2D ? d_means2D[id] : make_float4(0.f, 0.f, 0.f, 0.f);
+		const float m0 = m[0], m1 = m[1], m2z = m[2], s0 = s[0], s1 = s[1], s2 = s[2], o = d_opac[id], c0 = c[0], c1 = c[1];
+		const bool nz = m0 != 0.f || m1 != 0.f || m2z != 0.f || s0 != 0.f || s1 != 0.f || s2 != 0.f || o != 0.f || r.x != 0.f || r.y != 0.f ||
+				r.z != 0.f || r.w != 0.f || c0 != 0.f || c1 != 0.f || m2.x != 0.f || m2.y != 0.f || m2.z != 0.f || m2.w != 0.f;
+		if (!nz) continue;
+		const unsigned slot = atomicAdd(counter, 1u); // the header keeps counting past cap: the host sees the overflow
+		if (slot >= (unsigned)cap) continue;
+		float4 *row = packed + 5 * (size_t)slot + 5;
+		row[0] = make_float4(__uint_as_float((unsigned)id), m0, m1, m2z);
+		row[1] = make_float4(s0, s1, s2, o);
+		row[2] = r;
+		row[3] = make_float4(c0, c1, m2.x, m2.y);
+		row[4] = make_float4(m2.z, m2.w, 0.f, 0.f);
+	}
+}
+} // namespace
+
+extern "C" {
+size_t lgs_grad_rows_bytes(int cap) { return cap < 0 ? 0 : ((size_t)cap + 1) * 80; }
+
+int lgs_grad_pack_nonzero(int P, const float *dL_dmean3D, const float *dL_dscale, const float *dL_drot, const float *dL_dopacity,
+			  const float *dL_dcolor, const float *dL_dmeans2D, int cap, float *packed, void *stream)
+{
+	if (P < 0 || cap < 0 || !packed || (P && (!dL_dmean3D || !dL_dscale || !dL_drot || !dL_dopacity || !dL_dcolor))) return LGS_EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (cudaMemsetAsync(packed, 0, 80, st) != cudaSuccess) return LGS_ECUDA; // header row: {rows found, -}
+	if (P == 0) return 0;
+	grad_pack_nonzero_kernel<<<148 * 8, 256, 0, st>>>(P, dL_dmean3D, dL_dscale, dL_drot, dL_dopacity, dL_dcolor,
+							  (const float4 *)dL_dmeans2D, cap, (float4 *)packed);
+	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;
+}
+} // extern "C"
+
 // ---- densification statistics (the consumer of means2D.grad) --------------------------------------
 // Restates scene/gaussian_model.py:597-618 training_statis: per visible anchor, accumulate the clamped neural opacities
 // and the visit count; per rendered neural Gaussian (selected by the opacity mask AND visible in the frame, radii > 0),

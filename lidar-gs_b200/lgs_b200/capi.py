@@ -16,7 +16,8 @@ SYMBOLS = ["lgs_forward", "lgs_backward", "lgs_backward_scratch_bytes", "lgs_vis
            "lgs_set_rows_per_bin", "lgs_set_sort_all", "lgs_timing_enable", "lgs_timing_collect", "lgs_last_num_instances", "lgs_launch_count",
            "lgs_last_error", "lgs_version",
            "lgs_surfel_forward", "lgs_surfel_backward", "lgs_surfel_backward_scratch_bytes", "lgs_surfel_visible_filter",
-           "lgs_surfel_mark_visible", "lgs_backward_touched", "lgs_grad_pack_bytes", "lgs_grad_count", "lgs_grad_pack", "lgs_grad_scatter_add"]
+           "lgs_surfel_mark_visible", "lgs_backward_touched", "lgs_grad_pack_bytes", "lgs_grad_count", "lgs_grad_pack", "lgs_grad_scatter_add",
+           "lgs_grad_rows_bytes", "lgs_grad_pack_nonzero"]
 
 
 def load():
@@ -59,6 +60,10 @@ def load():
     L.lgs_grad_count.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.lgs_grad_pack.restype = i
     L.lgs_grad_pack.argtypes = [vp, vp, i, vp, vp, vp, vp, vp, vp, vp]
+    L.lgs_grad_rows_bytes.restype = C.c_size_t
+    L.lgs_grad_rows_bytes.argtypes = [i]
+    L.lgs_grad_pack_nonzero.restype = i
+    L.lgs_grad_pack_nonzero.argtypes = [i, vp, vp, vp, vp, vp, vp, i, vp, vp]
     L.lgs_grad_scatter_add.restype = i
     L.lgs_grad_scatter_add.argtypes = [i, vp, i, i, i, vp, vp, vp, vp, vp, vp]
     L.lgs_set_rows_per_bin.argtypes = [i]

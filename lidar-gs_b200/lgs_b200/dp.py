@@ -193,3 +193,56 @@ def _device_u32(ptr, dev):
     a = _A()
     a.__cuda_array_interface__ = dict(shape=(1,), typestr="<i4", data=(int(ptr), False), version=3)
     return torch.as_tensor(a, device=dev)
+
+
+# ---- sparse read-back of one frame's gradients (csrc/lgs_dp.cu: lgs_grad_pack_nonzero) ----
+ROW_FLOATS = 20   # id, dmean3D 3, dscale 3, dopacity, drot 4, dcolor 2, dmeans2D 4, pad 2
+
+
+def pack_nonzero_rows(grads, means2D_grad, cap, out=None):
+    """grads: dict means3D [P,3], scales [P,3], rotations [P,4], opacities [P,1], colors [P,2] (contiguous float32 CUDA);
+    means2D_grad [P,4] or None.  -> float32 CUDA tensor [(cap + 1), 20]: row 0 = header (first word, as int32: rows found),
+    then one row per Gaussian with a non-zero gradient.  Copy it to the host and hand it to unpack_rows()."""
+    import ctypes as C
+    from . import capi
+    L = capi.load()
+    m = grads["means3D"]
+    if not m.is_cuda:
+        raise RuntimeError("pack_nonzero_rows: CUDA tensors only (there is no CPU path)")
+    P, dev = m.shape[0], m.device
+    ts = [grads[k] for k in ("means3D", "scales", "rotations", "opacities", "colors")] + ([means2D_grad] if means2D_grad is not None else [])
+    for t_ in ts:
+        if not (t_.is_contiguous() and t_.dtype == torch.float32 and t_.shape[0] == P):
+            raise ValueError("pack_nonzero_rows: contiguous float32 [P, c] tensors expected")
+    if out is None:
+        out = torch.empty((cap + 1, ROW_FLOATS), dtype=torch.float32, device=dev)
+    assert out.numel() * 4 >= L.lgs_grad_rows_bytes(cap)
+    p = lambda t_: C.c_void_p(t_.data_ptr() if t_ is not None else 0)
+    with torch.cuda.device(dev):
+        rc = L.lgs_grad_pack_nonzero(P, p(grads["means3D"]), p(grads["scales"]), p(grads["rotations"]), p(grads["opacities"]),
+                                     p(grads["colors"]), p(means2D_grad), int(cap), p(out),
+                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    if rc < 0:
+        raise capi.LgsError("lgs_grad_pack_nonzero failed")
+    return out
+
+
+def unpack_rows(packed_host, P):
+    """Host side: the dense gradient arrays back from the rows (numpy).  -> (dict, found); found > capacity means rows were
+    dropped and the dense arrays have to be read instead."""
+    import numpy as np
+    a = np.asarray(packed_host, dtype=np.float32).reshape(-1, ROW_FLOATS)
+    found = int(a[0, :1].view(np.int32)[0])
+    n = min(found, a.shape[0] - 1)
+    rows = a[1:1 + n]
+    ids = rows[:, 0].view(np.int32) if rows.flags.c_contiguous else np.ascontiguousarray(rows[:, 0]).view(np.int32)
+    out = dict(means3D=np.zeros((P, 3), np.float32), scales=np.zeros((P, 3), np.float32), opacities=np.zeros((P, 1), np.float32),
+               rotations=np.zeros((P, 4), np.float32), colors=np.zeros((P, 2), np.float32), means2D=np.zeros((P, 4), np.float32))
+    out["means3D"][ids] = rows[:, 1:4]
+    out["scales"][ids] = rows[:, 4:7]
+    out["opacities"][ids] = rows[:, 7:8]
+    out["rotations"][ids] = rows[:, 8:12]
+    out["colors"][ids] = rows[:, 12:14]
+    out["means2D"][ids] = rows[:, 14:18]
+    return out, found
+

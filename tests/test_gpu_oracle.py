@@ -213,3 +213,41 @@ def test_sparse_gradient_exchange_equals_dense_sum():
         xs.scatter_add(gathered, 2, r, cap, views_of(got))
         torch.cuda.synchronize()
         assert torch.equal(got.flat, want) or float((got.flat - want).abs().max()) <= 1e-7 * float(want.abs().max())
+
+
+def test_sparse_gradient_readback_is_lossless():
+    """lgs_grad_pack_nonzero / dp.unpack_rows: the 80-byte rows of the Gaussians with a non-zero gradient rebuild every
+    dense gradient array of the operator (the 13 parameter gradients and the 4-column means2D holder) exactly; a buffer
+    that is too small reports how many rows there were."""
+    import torch
+    from lgs_b200 import capi, dp, synth
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(P=30000, H=16, W=256, seed=78, pose="random")
+    sc.update(synth.make_upstream(16, 256, seed=78))
+    P = sc["P"]
+    d = util.to_torch(sc, dev)
+    fr = capi.Frame(dev)
+    fr.forward(d["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"], d["viewmatrix"], d["beams"], 16, 256, 80, 0)
+    z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+    grads = dict(means3D=z(P, 3), scales=z(P, 3), rotations=z(P, 4), opacities=z(P, 1), colors=z(P, 2), means2D=z(P, 4), cov3D=None,
+                 scratch=torch.empty(capi.load().lgs_backward_scratch_bytes(P), dtype=torch.uint8, device=dev))
+    fr.backward(d["g_color"], d["g_depth"], d["g_occ"], grads=grads)
+    keys = ("means3D", "scales", "rotations", "opacities", "colors")
+    nz = (grads["means2D"] != 0).any(dim=1)
+    for k in keys:
+        nz |= (grads[k] != 0).any(dim=1)
+    want = int(nz.sum().item())
+    assert 0 < want < P
+    packed = dp.pack_nonzero_rows({k: grads[k] for k in keys}, grads["means2D"], want + 100)
+    back, found = dp.unpack_rows(packed.cpu().numpy(), P)
+    assert found == want
+    for k in keys + ("means2D",):
+        assert np.array_equal(back[k], grads[k].cpu().numpy()), k
+    # without the screen-space holder; and a buffer that is too small
+    back, found = dp.unpack_rows(dp.pack_nonzero_rows({k: grads[k] for k in keys}, None, P).cpu().numpy(), P)
+    assert found <= want and np.array_equal(back["means3D"], grads["means3D"].cpu().numpy()) and not back["means2D"].any()
+    small = dp.pack_nonzero_rows({k: grads[k] for k in keys}, grads["means2D"], 10)
+    _, found = dp.unpack_rows(small.cpu().numpy(), P)
+    assert found == want and small.shape[0] == 11
+    with pytest.raises(RuntimeError):
+        dp.pack_nonzero_rows({k: grads[k].cpu() for k in keys}, None, 10)
