@@ -113,3 +113,91 @@ def test_world2_allreduce_equals_serial_sum(with_stats):
         # same addends, different association (2 partial sums): fp32 round-off only
         assert np.abs(flat - ref).max() <= 1e-6 * np.abs(ref).max(), rank
     assert np.array_equal(got[0][1], got[1][1])  # replicas hold identical reduced gradients
+
+
+# ---- the sparse exchange's host protocol at world_size 2 (the three device kernels replaced by torch stand-ins) ----
+def _standins(xs, views, P):
+    """CPU restatements of lgs_grad_count / lgs_grad_pack / lgs_grad_scatter_add's row formats (include/lgs_rasterizer.h),
+    installed on ONE SparseExchange instance inside the test process: the product has no CPU path."""
+    names = ("means3D", "scales", "opacities", "rotations", "colors")     # column order of a 64-byte row after the id
+
+    def nonzero_ids():
+        nz = torch.zeros(P, dtype=torch.bool)
+        for n in names:
+            nz |= (views[n] != 0).any(dim=1)
+        return torch.nonzero(nz).reshape(-1)
+
+    def count_nonzero(ids_ptr, cnt_ptr, v, stream=None):
+        xs._cnt.fill_(int(nonzero_ids().numel()))
+        return xs._cnt
+
+    def pack(ids_ptr, cnt_ptr, cap, v, stream=None):
+        ids = nonzero_ids().flip(0)                                        # any order is allowed
+        out = torch.zeros((cap + 1, 16), dtype=torch.float32)
+        out[0, :1].view(torch.int32)[0] = ids.numel()
+        out[1:1 + ids.numel(), 0] = ids.to(torch.int32).view(torch.float32)
+        out[1:1 + ids.numel(), 1:14] = torch.cat([v[n][ids] for n in names], dim=1)
+        return out.reshape(-1)
+
+    def scatter_add(gathered, nranks, my_rank, cap, v, stream=None):
+        blocks = gathered.view(nranks, cap + 1, 16)
+        for r in range(nranks):
+            if r == my_rank:
+                continue
+            n = int(blocks[r, 0, :1].view(torch.int32)[0])
+            rows = blocks[r, 1:1 + n]
+            ids = rows[:, 0].contiguous().view(torch.int32).long()
+            o = 1
+            for name in names:
+                c = v[name].shape[1]
+                v[name].index_add_(0, ids, rows[:, o:o + c])
+                o += c
+
+    xs.touched = lambda scratch: (0, 0)
+    xs.count_nonzero, xs.pack, xs.scatter_add = count_nonzero, pack, scatter_add
+
+
+def _sparse_worker(rank, world, port, density, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        Pn = 4000
+        g = torch.Generator().manual_seed(500 + rank)
+        b = dp.GradBucket(Pn, "cpu")
+        rows = torch.nonzero(torch.rand(Pn, generator=g) < density).reshape(-1)   # this rank's frame touched these Gaussians
+        for name in dp.PARAM_LAYOUT:
+            b.views[name][rows] = torch.randn((rows.numel(), b.views[name].shape[1]), generator=g)
+        local = b.flat.clone()
+        xs = dp.SparseExchange(Pn, torch.device("cpu"))
+        views = {n: b.views[n] for n in dp.PARAM_LAYOUT}
+        _standins(xs, views, Pn)
+        xs.exchange(None, b.flat, views)
+        q.put((rank, local.numpy(), b.flat.numpy().copy(), dict(xs.last), int(rows.numel())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("density,mode", [(0.02, "sparse"), (0.9, "dense")])
+def test_world2_sparse_exchange_protocol(density, mode):
+    """Every rank ends with the sum of both ranks' gradients; few touched rows travel as an all-gather of packed rows sized by
+    the all-reduced maximum row count, many fall back to the dense all-reduce."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sparse_worker, args=(r, world, port, density, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=180) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = got[0][1] + got[1][1]
+    assert np.abs(want).max() > 0
+    for rank, _, summed, last, nrows in got:
+        assert np.allclose(summed, want, rtol=0, atol=1e-6), rank
+        assert last["mode"] == mode
+        if mode == "sparse":
+            assert last["rows"] % 1024 == 0 and last["rows"] >= max(g[4] for g in got)   # one capacity for everybody
+            assert last["bytes"] == world * (last["rows"] + 1) * 64 < 13 * 4000 * 4
+    assert got[0][3] == got[1][3]
