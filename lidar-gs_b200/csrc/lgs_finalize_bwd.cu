@@ -238,8 +238,10 @@ finalize_bwd_kernel(int P, const float *__restrict__ means3D, const float *__res
 
 namespace {
 
-// One CTA per bin: entries [0, deepest contributor of the bin) are what render_bwd replays.  The first CTA to
-// reach a Gaussian (atomicOr on its bit) zeroes its 80-byte accumulator row, so no P-sized memset is needed.
+// One CTA per bin: of the entries [0, deepest contributor of the bin) render_bwd replays those that forward flagged
+// as blended (spare word of the entry != 0).  The first CTA to reach such a Gaussian (atomicOr on its bit) zeroes
+// its 80-byte accumulator row, so no P-sized memset is needed and the finalize kernel only visits rows that
+// actually received a gradient.
 __global__ void __launch_bounds__(512)
 mark_touched_kernel(FrameGeom g, const uint32_t *__restrict__ binbase, const uint32_t *__restrict__ n_contrib,
 		    const uint4 *__restrict__ entries, float *__restrict__ grad, uint32_t *__restrict__ touched,
@@ -261,7 +263,9 @@ mark_touched_kernel(FrameGeom g, const uint32_t *__restrict__ binbase, const uin
 	__syncthreads();
 	const unsigned maxc = smax, base = binbase[bin];
 	for (unsigned i = tid; i < maxc; i += 512) {
-		const unsigned id = entries[base + i].y, bit = 1u << (id & 31);
+		const uint4 e = entries[base + i];
+		if (e.w == 0u) continue; // forward blended this entry into no pixel: backward never adds to its row
+		const unsigned id = e.y, bit = 1u << (id & 31);
 		if (!(atomicOr(&touched[id >> 5], bit) & bit)) {
 			tlist[atomicAdd(tcount, 1u)] = id;
 			float4 *row = reinterpret_cast<float4 *>(grad + (size_t)id * LGS_GRAD_STRIDE);
