@@ -1,8 +1,9 @@
 // lgs_abi.cu -- the extern "C" boundary declared in include/lgs_rasterizer.h: argument checks, scratch
 // carving, kernel sequencing on the caller's stream.  Mirrors the orchestration role of the
 // reference's CudaRasterizer::Rasterizer (R3 rasterizer_impl.cu:142-154, :202-358, :362-426,
-// :431-549) without its seven cudaDeviceSynchronize() calls: the only host wait left is the one
-// the interface itself demands (the scratch callback needs the instance count).
+// :431-549) without its seven cudaDeviceSynchronize() calls and without its blocking read-back of num_rendered in
+// the middle of the frame: the one host wait left (the interface returns num_rendered) is on an event recorded after
+// the scan and overlaps the scatter and compositing kernels, which are already enqueued.
 #include "../../include/lgs_rasterizer.h"
 #include "lgs_kernels.h"
 
@@ -14,16 +15,26 @@
 namespace {
 
 thread_local char g_err[512] = "";
-thread_local FrameTotals *g_pinned = nullptr;     // mapped pinned host memory the scan kernel writes the frame totals into
-thread_local FrameTotals *g_pinned_dev = nullptr; // its device-side address
 thread_local long long g_last_instances = 0;
-// side stream for work that is independent of the main dependency chain (zero-fill of the API gradients while the
-// gradient kernel runs); forked from and joined back into the caller's stream with events
-thread_local cudaStream_t g_side = nullptr;
-thread_local cudaEvent_t g_fork = nullptr, g_join = nullptr;
+thread_local long long g_overflow_reruns = 0;
+// Per (host thread, device) state: mapped pinned host memory the scan kernel writes the frame totals into, the event
+// the host waits on to read them, a side stream for work that is independent of the main dependency chain (zero-fill
+// of the API gradients while the gradient kernel runs; forked from and joined back into the caller's stream with
+// events), and the high-water mark the binning buffer of the next frame is sized from.
+struct DevState {
+	bool init = false;
+	FrameTotals *pinned = nullptr, *pinned_dev = nullptr;
+	cudaEvent_t scan_done = nullptr;
+	cudaStream_t side = nullptr;
+	cudaEvent_t fork = nullptr, join = nullptr;
+	struct Hwm { int P = -1, W = 0, H = 0; long long N = 0; } hwm[2]; // [0] 3-D path, [1] surfel path
+};
+#define LGS_MAX_DEVICES 64
+thread_local DevState g_dev[LGS_MAX_DEVICES];
 std::atomic<int> g_rows_per_bin{0};
 std::atomic<int> g_sort_all{0};
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_capacity_hint{0}; // test knob: forces the capacity guess of the next frames (0 = automatic)
 
 // ---- optional per-stage CUDA-event timing (bench.py's roofline leg) ---------------------------
 struct StageTimer {
@@ -73,15 +84,124 @@ int pick_rows_per_bin(int H)
 	return rb;
 }
 
-FrameGeom make_geom(int P, int W, int H)
+FrameGeom make_geom(int P, int W, int H, int RB = 0)
 {
 	FrameGeom g;
 	g.P = P; g.W = W; g.H = H;
 	g.gx = (W + LGS_TILE_X_ - 1) / LGS_TILE_X_;
-	g.RB = pick_rows_per_bin(H);
+	g.RB = RB > 0 ? RB : pick_rows_per_bin(H);
 	g.nrg = (H + g.RB - 1) / g.RB;
 	g.nbins = g.gx * g.nrg;
 	return g;
+}
+
+// The scratch layout depends on rows_per_bin, a knob that may change between a forward call and its backward call:
+// remember which value each recent geometry buffer was carved with (backward falls back to the current knob for a
+// buffer it has never seen, e.g. one copied by the caller).
+struct GeomTag { const void *geom; int RB; };
+thread_local GeomTag g_geom_tags[16];
+thread_local int g_geom_tag_next = 0;
+void remember_rows_per_bin(const void *geom, int RB)
+{
+	g_geom_tags[g_geom_tag_next] = {geom, RB};
+	g_geom_tag_next = (g_geom_tag_next + 1) % 16;
+}
+int recall_rows_per_bin(const void *geom)
+{
+	for (int i = 0; i < 16; i++) {
+		const GeomTag &t = g_geom_tags[(g_geom_tag_next + 15 - i) % 16]; // most recent first
+		if (t.geom == geom && t.RB > 0) return t.RB;
+	}
+	return 0;
+}
+
+// lazily created per-device state of the calling thread (nullptr + error message on failure)
+DevState *dev_state()
+{
+	int d = 0;
+	if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= LGS_MAX_DEVICES) {
+		fail(LGS_ECUDA, "cudaGetDevice failed or device index out of range");
+		return nullptr;
+	}
+	DevState &ds = g_dev[d];
+	if (!ds.init) {
+		cudaError_t e;
+		if ((e = cudaHostAlloc((void **)&ds.pinned, sizeof(FrameTotals), cudaHostAllocMapped)) != cudaSuccess ||
+		    (e = cudaHostGetDevicePointer((void **)&ds.pinned_dev, ds.pinned, 0)) != cudaSuccess ||
+		    (e = cudaEventCreateWithFlags(&ds.scan_done, cudaEventDisableTiming)) != cudaSuccess ||
+		    (e = cudaStreamCreateWithFlags(&ds.side, cudaStreamNonBlocking)) != cudaSuccess ||
+		    (e = cudaEventCreateWithFlags(&ds.fork, cudaEventDisableTiming)) != cudaSuccess ||
+		    (e = cudaEventCreateWithFlags(&ds.join, cudaEventDisableTiming)) != cudaSuccess) {
+			fail(LGS_ECUDA, "per-device state", e);
+			return nullptr;
+		}
+		ds.init = true;
+	}
+	return &ds;
+}
+
+// Binning, shared by the 3-D and the surfel path.  The reference reads num_rendered back with a blocking copy BEFORE it
+// can size its binning buffer and launch anything else (rasterizer_impl.cu:288-300).  Here the buffer is sized from a
+// high-water mark (the previous frame of the same shape + 25 %), everything up to and including the compositing kernel is
+// enqueued without waiting, and only then does the host wait -- for the scan, not for the stream -- to read the totals
+// the scan kernel stored in mapped host memory: the wait overlaps scatter + render.  If the guess was too small the scan
+// sets a device-side flag that turns scatter and render into no-ops, and the frame is re-run once with the exact size.
+//   project(ranks, capacity) : enqueue the projection kernel          render(entries) : enqueue the compositing kernel
+template <class ProjectFn, class RenderFn>
+int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_fn binning_buffer, void *binning_user, int far,
+		   int near, cudaStream_t st, ProjectFn project, RenderFn render, unsigned long long *R_out)
+{
+	DevState *ds = dev_state();
+	if (!ds) return LGS_ECUDA;
+	DevState::Hwm &hw = ds->hwm[path];
+	size_t cap;
+	if (g_capacity_hint.load() > 0) cap = (size_t)g_capacity_hint.load();
+	else if (hw.P == g.P && hw.W == g.W && hw.H == g.H && hw.N > 0) cap = (size_t)hw.N + (size_t)hw.N / 4 + 4096;
+	else cap = 4 * (size_t)g.P + 4096;
+	for (int attempt = 0;; attempt++) {
+		if (cap > 0xfffffff0ull) return fail(LGS_EINVAL, "binning buffer would exceed 2^32 instances");
+		const size_t ranks_off = lgs_al(cap * sizeof(uint4));
+		char *bb = binning_buffer(ranks_off + cap * sizeof(uint32_t), binning_user);
+		if (!bb) return fail(LGS_ENOMEM, "binning callback returned NULL");
+		uint4 *entries = (uint4 *)bb;
+		uint32_t *ranks = (uint32_t *)(bb + ranks_off);
+		g_timer.begin(LGS_STAGE_CLEAR, st);
+		CK(cudaMemsetAsync(gp.cnt, 0, (size_t)g.nbins * LGS_NB * 4, st));
+		CK(cudaMemsetAsync(gp.totals, 0, sizeof(FrameTotals), st));
+		g_timer.end(st);
+		g_timer.begin(LGS_STAGE_PROJECT, st);
+		project(ranks, (unsigned)cap);
+		g_timer.end(st);
+		g_timer.begin(LGS_STAGE_SCAN, st);
+		lgs_launch_scan(g, gp, ds->pinned_dev, (unsigned)cap, st);
+		g_timer.end(st);
+		CK(cudaEventRecord(ds->scan_done, st));
+		g_timer.begin(LGS_STAGE_SCATTER, st);
+		lgs_launch_scatter(g, gp, entries, ranks, (unsigned)cap, far, near, st);
+		g_timer.end(st);
+		g_timer.begin(LGS_STAGE_RENDER_FWD, st);
+		render(entries);
+		g_timer.end(st);
+		g_launches += 5;
+		CK(cudaGetLastError());
+		// the scan kernel stored the totals straight into mapped host memory (a memcpy would queue behind whatever bulk
+		// device-to-host transfer the application has in flight on the copy engine); scatter + render keep running
+		CK(cudaEventSynchronize(ds->scan_done));
+		const unsigned long long N = ds->pinned->num_instances;
+		*R_out = ds->pinned->num_rendered;
+		g_last_instances = (long long)N;
+		if (N <= cap) {
+			hw.P = g.P; hw.W = g.W; hw.H = g.H;
+			hw.N = (long long)N;
+			return 0;
+		}
+		if (attempt >= 1) return fail(LGS_ECUDA, "binning buffer overflow after re-sizing (internal error)");
+		// too small: scatter and render saw the overflow flag and did nothing.  Wait for them (the buffer is about to be
+		// replaced), then run the frame again with the exact size.
+		CK(cudaStreamSynchronize(st));
+		g_overflow_reruns++;
+		cap = (size_t)N;
+	}
 }
 
 } // namespace
@@ -125,48 +245,22 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn 
 	if (!gb || !ib) return fail(LGS_ENOMEM, "lgs_forward: scratch callback returned NULL");
 	GeomPtrs gp = lgs_carve_geom(gb, g);
 	ImagePtrs ip = lgs_carve_image(ib, g);
+	remember_rows_per_bin(gb, g.RB);
 
-	if (!g_pinned) {
-		CK(cudaHostAlloc((void **)&g_pinned, sizeof(FrameTotals), cudaHostAllocMapped));
-		CK(cudaHostGetDevicePointer((void **)&g_pinned_dev, g_pinned, 0));
-	}
-
-	g_timer.begin(LGS_STAGE_CLEAR, st);
-	CK(cudaMemsetAsync(gp.cnt, 0, (size_t)g.nbins * LGS_NB * 4, st));
-	CK(cudaMemsetAsync(gp.totals, 0, sizeof(FrameTotals), st));
-	g_timer.end(st);
-	g_timer.begin(LGS_STAGE_PROJECT, st);
-	lgs_launch_project(g, means3D, scales, scale_modifier, rotations, cov3D_precomp, opacities, colors_precomp,
-			   viewmatrix, beam_inclinations, far, near, gp, radii, radii_xy, st);
-	g_timer.end(st);
-	g_timer.begin(LGS_STAGE_SCAN, st);
-	lgs_launch_scan(g, gp, g_pinned_dev, st);
-	g_timer.end(st);
-	g_launches += 3;
-	CK(cudaGetLastError());
-	// the scan kernel stored the totals straight into mapped host memory (a memcpy would queue behind whatever
-	// bulk device-to-host transfer the application has in flight on the copy engine)
-	CK(cudaStreamSynchronize(st));
-	const unsigned N = g_pinned->num_instances;
-	const unsigned long long R = g_pinned->num_rendered;
-	g_last_instances = N;
+	unsigned long long R = 0;
+	const int rc = bin_and_render(
+		0, g, gp, binning_buffer, binning_user, far, near, st,
+		[&](uint32_t *ranks, unsigned cap) {
+			lgs_launch_project(g, means3D, scales, scale_modifier, rotations, cov3D_precomp, opacities, colors_precomp,
+					   viewmatrix, beam_inclinations, far, near, gp, radii, radii_xy, ranks, cap, st);
+		},
+		[&](uint4 *entries) {
+			lgs_launch_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_depth, out_occ,
+					      g_sort_all.load(), st);
+		},
+		&R);
+	if (rc < 0) return rc;
 	if (R > 0x7fffffffULL) return fail(LGS_EINVAL, "lgs_forward: num_rendered overflows int");
-
-	char *bb = binning_buffer((size_t)(N ? N : 1) * sizeof(uint4), binning_user);
-	if (!bb) return fail(LGS_ENOMEM, "lgs_forward: binning callback returned NULL");
-	uint4 *entries = (uint4 *)bb;
-	if (N) {
-		g_timer.begin(LGS_STAGE_SCATTER, st);
-		lgs_launch_scatter(g, gp, entries, N, st);
-		g_timer.end(st);
-		g_launches += 1;
-	}
-	g_timer.begin(LGS_STAGE_RENDER_FWD, st);
-	lgs_launch_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_depth, out_occ,
-			      g_sort_all.load(), st);
-	g_timer.end(st);
-	g_launches += 1;
-	CK(cudaGetLastError());
 	if (debug) CK(cudaStreamSynchronize(st));
 	return (int)R;
 }
@@ -199,7 +293,7 @@ int lgs_backward(int P, int D, int M, int R, const float *background, int width,
 		return fail(LGS_EINVAL, "lgs_backward: null input");
 	if (!cov3D_precomp && (!scales || !rotations)) return fail(LGS_EINVAL, "lgs_backward: need scales+rotations or cov3D_precomp");
 
-	FrameGeom g = make_geom(P, width, height);
+	FrameGeom g = make_geom(P, width, height, recall_rows_per_bin(geom_buffer));
 	GeomPtrs gp = lgs_carve_geom(geom_buffer, g);
 	ImagePtrs ip = lgs_carve_image(image_buffer, g);
 	g_timer.begin(LGS_STAGE_CLEAR, st);
@@ -211,11 +305,10 @@ int lgs_backward(int P, int D, int M, int R, const float *background, int width,
 	g_timer.end(st);
 	// every API gradient of an untouched Gaussian is zero: plain memsets, issued on a side stream so that they
 	// overlap the (compute-bound) gradient kernel; the finalize kernel, which only visits the list, waits for them
-	if (!g_side) {
-		CK(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
-		CK(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
-		CK(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
-	}
+	DevState *ds = dev_state();
+	if (!ds) return LGS_ECUDA;
+	cudaStream_t g_side = ds->side;
+	cudaEvent_t g_fork = ds->fork, g_join = ds->join;
 	CK(cudaEventRecord(g_fork, st));
 	CK(cudaStreamWaitEvent(g_side, g_fork, 0));
 	CK(cudaMemsetAsync(dL_dmean2D, 0, (size_t)P * 16, g_side));
@@ -320,42 +413,21 @@ int lgs_surfel_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_al
 	if (!gb || !ib) return fail(LGS_ENOMEM, "lgs_surfel_forward: scratch callback returned NULL");
 	GeomPtrs gp = lgs_carve_geom(gb, g, 16 * LGS_SREC);
 	SurfelImagePtrs ip = lgs_carve_surfel_image(ib, g);
-	if (!g_pinned) {
-		CK(cudaHostAlloc((void **)&g_pinned, sizeof(FrameTotals), cudaHostAllocMapped));
-		CK(cudaHostGetDevicePointer((void **)&g_pinned_dev, g_pinned, 0));
-	}
-	g_timer.begin(LGS_STAGE_CLEAR, st);
-	CK(cudaMemsetAsync(gp.cnt, 0, (size_t)g.nbins * LGS_NB * 4, st));
-	CK(cudaMemsetAsync(gp.totals, 0, sizeof(FrameTotals), st));
-	g_timer.end(st);
-	g_timer.begin(LGS_STAGE_PROJECT, st);
-	lgs_launch_surfel_project(g, means3D, scales, scale_modifier, rotations, opacities, colors_precomp, viewmatrix,
-				  beam_inclinations, far, near, gp, radii, radii_xy, st);
-	g_timer.end(st);
-	g_timer.begin(LGS_STAGE_SCAN, st);
-	lgs_launch_scan(g, gp, g_pinned_dev, st);
-	g_timer.end(st);
-	g_launches += 3;
-	CK(cudaGetLastError());
-	CK(cudaStreamSynchronize(st)); // the binning callback needs the instance count (see lgs_forward)
-	const unsigned N = g_pinned->num_instances;
-	const unsigned long long R = g_pinned->num_rendered;
-	g_last_instances = N;
+	remember_rows_per_bin(gb, g.RB);
+	unsigned long long R = 0;
+	const int rc = bin_and_render(
+		1, g, gp, binning_buffer, binning_user, far, near, st,
+		[&](uint32_t *ranks, unsigned cap) {
+			lgs_launch_surfel_project(g, means3D, scales, scale_modifier, rotations, opacities, colors_precomp, viewmatrix,
+						  beam_inclinations, far, near, gp, radii, radii_xy, ranks, cap, st);
+		},
+		[&](uint4 *entries) {
+			lgs_launch_surfel_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_others,
+						     g_sort_all.load(), st);
+		},
+		&R);
+	if (rc < 0) return rc;
 	if (R > 0x7fffffffULL) return fail(LGS_EINVAL, "lgs_surfel_forward: num_rendered overflows int");
-	char *bb = binning_buffer((size_t)(N ? N : 1) * sizeof(uint4), binning_user);
-	if (!bb) return fail(LGS_ENOMEM, "lgs_surfel_forward: binning callback returned NULL");
-	uint4 *entries = (uint4 *)bb;
-	if (N) {
-		g_timer.begin(LGS_STAGE_SCATTER, st);
-		lgs_launch_scatter(g, gp, entries, N, st);
-		g_timer.end(st);
-		g_launches += 1;
-	}
-	g_timer.begin(LGS_STAGE_RENDER_FWD, st);
-	lgs_launch_surfel_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_others, g_sort_all.load(), st);
-	g_timer.end(st);
-	g_launches += 1;
-	CK(cudaGetLastError());
 	if (debug) CK(cudaStreamSynchronize(st));
 	return (int)R;
 }
@@ -382,7 +454,7 @@ int lgs_surfel_backward(int P, int D, int M, int R, const float *background, int
 		return fail(LGS_EINVAL, "lgs_surfel_backward: null output");
 	if (!means3D || !viewmatrix || !beam_inclinations || !background || !radii || !scales || !rotations)
 		return fail(LGS_EINVAL, "lgs_surfel_backward: null input");
-	FrameGeom g = make_geom(P, width, height);
+	FrameGeom g = make_geom(P, width, height, recall_rows_per_bin(geom_buffer));
 	if (g.RB > 8) { g.RB = 8; g.nrg = (height + 7) / 8; g.nbins = g.gx * g.nrg; }
 	GeomPtrs gp = lgs_carve_geom(geom_buffer, g, 16 * LGS_SREC);
 	SurfelImagePtrs ip = lgs_carve_surfel_image(image_buffer, g);
@@ -474,6 +546,13 @@ int lgs_timing_collect(double *ms_per_stage, long long *launches_per_stage)
 	return 0;
 }
 long long lgs_last_num_instances(void) { return g_last_instances; }
+long long lgs_overflow_reruns(void) { return g_overflow_reruns; }
+int lgs_set_capacity_hint(long long instances)
+{
+	if (instances < 0) return fail(LGS_EINVAL, "lgs_set_capacity_hint: negative capacity");
+	g_capacity_hint.store(instances);
+	return 0;
+}
 long long lgs_launch_count(void) { return g_launches.load(); }
 const char *lgs_last_error(void) { return g_err; }
 const char *lgs_version(void) { return "lgs_b200 0.1 (sm_100a)"; }

@@ -1,7 +1,8 @@
 // lgs_bin.cu -- depth-bucketed binning: replaces the reference's inclusive scan + duplicateWithKeys +
 // global 64-bit radix sort + identifyTileRanges (R3 rasterizer_impl.cu:70-139, :288-331) with
 //   scan   : (bin, depth-bucket) counts -> offsets            (2 tiny launches)
-//   scatter: one 16-B entry per (Gaussian, bin) straight into its (bin, bucket) segment
+//   scatter: one 16-B entry per (Gaussian, bin) straight into its (bin, bucket) segment, at the rank the projection
+//            kernel's counting atomic returned (rank stream): no atomics, no cursors
 // Ordering inside a bucket is settled later, lazily, by the compositing kernel (lgs_render_fwd.cu);
 // buckets are monotone in depth so bucket-major order + in-bucket sort on (depth bits, idx) is the
 // order the reference's stable radix sort on tile|depth produces.
@@ -44,7 +45,7 @@ scan_bins_kernel(int nbins, uint32_t *__restrict__ cnt, uint32_t *__restrict__ l
 // single block: exclusive scan of the per-bin totals (in place: binbase[b] holds total on entry)
 __global__ void __launch_bounds__(1024)
 scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__restrict__ totals, uint32_t *__restrict__ order,
-		  FrameTotals *__restrict__ host_totals)
+		  FrameTotals *__restrict__ host_totals, unsigned capacity)
 {
 	__shared__ unsigned wsum[32];
 	__shared__ unsigned carry_s;
@@ -72,9 +73,13 @@ scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__rest
 	if (threadIdx.x == 0) {
 		binbase[nbins] = carry_s;
 		totals->num_instances = carry_s;
-		if (host_totals) { // mapped pinned host memory: the host reads the counts after a stream sync, no copy engine involved
+		// the binning buffer was sized from a high-water mark before the count was known: if it is too small, every
+		// later kernel of the frame returns at once (they test this flag) and the host re-runs the frame
+		totals->overflow = carry_s > capacity ? 1u : 0u;
+		if (host_totals) { // mapped pinned host memory: the host reads the counts after waiting for an event, no copy engine involved
 			FrameTotals t = *totals;
 			t.num_instances = carry_s;
+			t.overflow = carry_s > capacity ? 1u : 0u;
 			*host_totals = t;
 			__threadfence_system();
 		}
@@ -110,31 +115,32 @@ scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__rest
 }
 
 // One thread per Gaussian; a Gaussian with a large footprint (near range: hundreds of bins) is expanded by its
-// whole warp, so no lane serialises a long loop while 31 others wait.
+// whole warp, so no lane serialises a long loop while 31 others wait.  Instance i of a Gaussian is bin
+// (g0 + i / nx, x0 + i % nx) -- the order in which lgs_emit_instances filed the ranks.
 #define LGS_COOP_MIN 12
 __global__ void __launch_bounds__(256)
-scatter_kernel(int P, int gx, int RB, const uint4 *__restrict__ aux, uint32_t *__restrict__ cursor,
+scatter_kernel(int P, int gx, int RB, int far_, int near_, const uint4 *__restrict__ aux, const uint32_t *__restrict__ ranks,
 	       const uint32_t *__restrict__ loc, const uint32_t *__restrict__ binbase, uint4 *__restrict__ entries,
-	       unsigned capacity, FrameTotals *__restrict__ totals)
+	       unsigned capacity, const FrameTotals *__restrict__ totals)
 {
+	if (totals->overflow) return; // the buffer is too small for this frame: the host re-runs it
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
 	uint4 a = make_uint4(0, 0, 0, 0);
 	if (idx < P) a = aux[idx];
 	int x0 = a.x & 0xffff, nx = (int)(a.x >> 16) - x0, y0 = a.y & 0xffff, y1 = a.y >> 16;
 	int g0 = y0 / RB, ng = nx > 0 ? (y1 - 1) / RB - g0 + 1 : 0;
 	int n = nx > 0 ? nx * ng : 0;
-	unsigned overflow = 0;
-	auto emit = [&](int x0_, int nx_, int g0_, unsigned bucket, const uint4 &e, int i) {
+	const unsigned bucket = (unsigned)lgs_depth_bucket(__uint_as_float(a.z), far_, near_);
+	auto emit = [&](int x0_, int nx_, int g0_, unsigned bucket_, unsigned soff_, const uint4 &e, int i) {
 		const int g = g0_ + i / nx_, x = x0_ + i - (i / nx_) * nx_;
-		const size_t bb = (size_t)(g * gx + x) * LGS_NB + bucket;
-		const unsigned pos = binbase[g * gx + x] + loc[bb] + atomicAdd(&cursor[bb], 1u);
+		const size_t bb = (size_t)(g * gx + x) * LGS_NB + bucket_;
+		const unsigned pos = binbase[g * gx + x] + loc[bb] + ranks[soff_ + i];
 		if (pos < capacity) entries[pos] = e;
-		else overflow++;
 	};
 	const uint4 e = make_uint4(a.z, (unsigned)idx, a.y, 0u);
 	if (n < LGS_COOP_MIN) {
 #pragma unroll 4
-		for (int i = 0; i < n; i++) emit(x0, nx, g0, a.w, e, i);
+		for (int i = 0; i < n; i++) emit(x0, nx, g0, bucket, a.w, e, i);
 	}
 	unsigned big = __ballot_sync(0xffffffffu, n >= LGS_COOP_MIN);
 	while (big) {
@@ -142,26 +148,26 @@ scatter_kernel(int P, int gx, int RB, const uint4 *__restrict__ aux, uint32_t *_
 		big &= big - 1;
 		const int sx0 = __shfl_sync(0xffffffffu, x0, src), snx = __shfl_sync(0xffffffffu, nx, src);
 		const int sg0 = __shfl_sync(0xffffffffu, g0, src), sn = __shfl_sync(0xffffffffu, n, src);
-		const unsigned sb = __shfl_sync(0xffffffffu, a.w, src);
+		const unsigned sb = __shfl_sync(0xffffffffu, bucket, src), so = __shfl_sync(0xffffffffu, a.w, src);
 		uint4 se;
 		se.x = __shfl_sync(0xffffffffu, e.x, src); se.y = __shfl_sync(0xffffffffu, e.y, src);
 		se.z = __shfl_sync(0xffffffffu, e.z, src); se.w = 0u;
-		for (int i = lane; i < sn; i += 32) emit(sx0, snx, sg0, sb, se, i);
+		for (int i = lane; i < sn; i += 32) emit(sx0, snx, sg0, sb, so, se, i);
 	}
-	if (overflow) atomicAdd(&totals->overflow, overflow);
 }
 
 } // namespace
 
-void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, cudaStream_t st)
+void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, unsigned capacity, cudaStream_t st)
 {
 	int warps_per_block = 8;
 	scan_bins_kernel<<<(g.nbins + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(g.nbins, gp.cnt, gp.loc, gp.binbase);
-	scan_total_kernel<<<1, 1024, 0, st>>>(g.nbins, gp.binbase, gp.totals, gp.order, host_totals);
+	scan_total_kernel<<<1, 1024, 0, st>>>(g.nbins, gp.binbase, gp.totals, gp.order, host_totals, capacity);
 }
 
-void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, unsigned capacity, cudaStream_t st)
+void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, const uint32_t *ranks, unsigned capacity,
+			int far_, int near_, cudaStream_t st)
 {
-	scatter_kernel<<<(g.P + 255) / 256, 256, 0, st>>>(g.P, g.gx, g.RB, gp.aux, gp.cnt, gp.loc, gp.binbase, entries,
+	scatter_kernel<<<(g.P + 255) / 256, 256, 0, st>>>(g.P, g.gx, g.RB, far_, near_, gp.aux, ranks, gp.loc, gp.binbase, entries,
 							  capacity, gp.totals);
 }

@@ -8,16 +8,17 @@
 void lgs_launch_project(const FrameGeom &g, const float *means3D, const float *scales, float mod,
 			const float *rotations, const float *cov3D_precomp, const float *opacities,
 			const float *colors, const float *view, const float *beams, int far_, int near_,
-			const GeomPtrs &gp, int *radii, int *radii_xy, cudaStream_t st);
+			const GeomPtrs &gp, int *radii, int *radii_xy, uint32_t *ranks, unsigned capacity, cudaStream_t st);
 void lgs_launch_filter(int P, const float *means3D, const float *scales, float mod, const float *rotations,
 		       const float *cov3D_precomp, const float *view, int W, int H, const float *beams, int far_,
 		       int near_, int *radii, int *radii_xy, cudaStream_t st);
 void lgs_launch_mark_visible(int P, const float *means3D, const float *view, unsigned char *present, cudaStream_t st);
 
-// bucket counts -> per-bin exclusive offsets (loc), bin bases (binbase), totals->num_instances; cnt reset to 0
-void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, cudaStream_t st);
-// (Gaussian, bin) instances -> entries[], bin-major / bucket-minor, unordered inside a bucket
-void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, unsigned capacity, cudaStream_t st);
+// bucket counts -> per-bin exclusive offsets (loc), bin bases (binbase), totals->num_instances / overflow; cnt reset to 0
+void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, unsigned capacity, cudaStream_t st);
+// (Gaussian, bin) instances -> entries[], bin-major / bucket-minor, unordered inside a bucket; positions from the rank stream
+void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, const uint32_t *ranks, unsigned capacity,
+			int far_, int near_, cudaStream_t st);
 
 void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries,
 			   const float *bg, const float *beams, float *out_color, float *out_depth, float *out_occ,
@@ -37,7 +38,8 @@ void lgs_launch_finalize_bwd(const FrameGeom &g, const float *means3D, const flo
 #include "lgs_surfel.cuh"
 void lgs_launch_surfel_project(const FrameGeom &g, const float *means3D, const float *scales, float mod, const float *rotations,
 			       const float *opacities, const float *colors, const float *view, const float *beams, int far_,
-			       int near_, const GeomPtrs &gp, int *radii, int *radii_xy, cudaStream_t st);
+			       int near_, const GeomPtrs &gp, int *radii, int *radii_xy, uint32_t *ranks, unsigned capacity,
+			       cudaStream_t st);
 void lgs_launch_surfel_filter(int P, const float *means3D, const float *scales, float mod, const float *rotations,
 			      const float *view, int W, int H, const float *beams, int far_, int near_, int *radii, int *radii_xy,
 			      cudaStream_t st);

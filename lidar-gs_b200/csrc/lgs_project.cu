@@ -1,5 +1,6 @@
 // lgs_project.cu -- per-Gaussian range-view ("laser beam") projection, fused with record packing,
-// depth-bucket counting and the num_rendered reduction.
+// depth-bucket counting (+ the rank stream that makes the scatter atomic-free) and the num_rendered reduction;
+// inputs staged through shared memory by TMA bulk copies.
 //
 // Restates R3 forward.cu:257-384 (preprocessCUDA) / :389-497 (filter_preprocessCUDA) with
 // computeCov3D :216-253, _proj_2basis :95-119, computeCov2D_lidar :146-169, find_closest_label
@@ -35,10 +36,8 @@ struct Projected {
 // Shared by render-forward (FILTER = false) and the anchor pre-filter (FILTER = true: the one
 // deliberate difference is the double-precision atan2 guard of fwd.cu:456).
 template <bool FILTER>
-__device__ __forceinline__ bool project_gaussian(int idx, const float *__restrict__ orig_points,
-						 const float *__restrict__ scales, float mod,
-						 const float *__restrict__ rotations,
-						 const float *__restrict__ cov3D_precomp,
+__device__ __forceinline__ bool project_gaussian(float px, float py, float pz, const float *cov_or_null, float s0, float s1,
+						 float s2, float mod, float4 rq,
 						 const float *__restrict__ view, int W, int H,
 						 const float *__restrict__ beams, const float *__restrict__ tanrow, float tanW,
 						 int far_, int near_, int gx, int gy, Projected &o)
@@ -48,7 +47,6 @@ __device__ __forceinline__ bool project_gaussian(int idx, const float *__restric
 	// Every expression below that ptxas could contract into an FMA is written with explicit _rn intrinsics in
 	// the order the reference's sm_100a SASS uses (preprocessCUDA 0x410-0x1d90: a0*b0 + a1*b1 + a2*b2 is
 	// fma(a2, b2, fma(a0, b0, fl(a1*b1))) throughout), so the record is bit-identical to the reference's state.
-	const float px = orig_points[3 * idx], py = orig_points[3 * idx + 1], pz = orig_points[3 * idx + 2];
 	float3 p_view = { // aux.h:94-102 transformPoint4x3
 		__fadd_rn(lgs_dot3m(px, view[0], py, view[4], pz, view[8]), view[12]),
 		__fadd_rn(lgs_dot3m(px, view[1], py, view[5], pz, view[9]), view[13]),
@@ -58,13 +56,12 @@ __device__ __forceinline__ bool project_gaussian(int idx, const float *__restric
 	if (dist >= far_ || dist <= near_) return false;
 
 	float cov3D[6];
-	if (cov3D_precomp != nullptr) {
+	if (cov_or_null != nullptr) {
 #pragma unroll
-		for (int k = 0; k < 6; k++) cov3D[k] = cov3D_precomp[6 * idx + k];
+		for (int k = 0; k < 6; k++) cov3D[k] = cov_or_null[k];
 	} else {
 		Cov3D cv3;
-		lgs_cov3d_from_scale_rot(scales[3 * idx + 0], scales[3 * idx + 1], scales[3 * idx + 2], mod, rotations[4 * idx + 0],
-					 rotations[4 * idx + 1], rotations[4 * idx + 2], rotations[4 * idx + 3], cv3);
+		lgs_cov3d_from_scale_rot(s0, s1, s2, mod, rq.x, rq.y, rq.z, rq.w, cv3);
 #pragma unroll
 		for (int k = 0; k < 6; k++) cov3D[k] = cv3.c[k];
 	}
@@ -156,13 +153,6 @@ __device__ __forceinline__ bool project_gaussian(int idx, const float *__restric
 	return true;
 }
 
-__device__ __forceinline__ int depth_bucket(float depth, int far_, int near_)
-{
-	float t = (depth - (float)near_) * ((float)LGS_NB / (float)(far_ - near_));
-	int b = (int)t;
-	return min(LGS_NB - 1, max(0, b));
-}
-
 // beam table + per-row tangents in shared memory (falls back to the global table when H is too large)
 #define LGS_MAX_SMEM_ROWS 2048
 __device__ __forceinline__ void load_beam_tables(const float *__restrict__ beams, int H, int W, float *sb, float *st,
@@ -185,107 +175,207 @@ __device__ __forceinline__ void load_beam_tables(const float *__restrict__ beams
 	}
 }
 
-__global__ void __launch_bounds__(256)
-project_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ scales, float mod,
+// ---- staged, persistent projection kernels ----------------------------------------------------------------------
+// A CTA walks tiles of PRJ_TILE consecutive Gaussians.  The inputs of a tile are CONTIGUOUS spans of the attribute
+// arrays (xyz 12 B, scale 12 B, quaternion 16 B -- or cov3D 24 B --, opacity 4 B, features 8 B per Gaussian), so one
+// elected thread moves them into shared memory with 1-D bulk copies (TMA, cp.async.bulk) that complete on an
+// mbarrier, two tiles deep: the copy of tile i + 1 is in flight while tile i is projected, and every global read is a
+// full-line burst instead of the stride-3 / stride-4 scalar loads of a thread-per-Gaussian AoS read (the reference's
+// pattern, fwd.cu:298-316).  Shared-memory reads are conflict-free (stride 3 words is odd; quaternions as LDS.128).
+// Bulk copies need 16-byte aligned addresses and sizes: the < 16 B tail of a partial last tile is copied by the
+// elected thread, and arrays that are not 16-byte aligned fall back to cooperative coalesced loads into the same
+// staging layout (use_tma = 0).
+#define PRJ_TILE 256
+#define PRJ_STAGES 2
+struct PrjStage { // byte offsets inside one staging buffer
+	static constexpr int XYZ = 0, SC = XYZ + 12 * PRJ_TILE, ROT = SC + 12 * PRJ_TILE, // cov3D (24 B) overlays SC + ROT
+			     OPA = ROT + 16 * PRJ_TILE, COL = OPA + 4 * PRJ_TILE, BYTES = COL + 8 * PRJ_TILE;
+};
+#define PRJ_HDR 128 // mbarriers
+
+// Thread 0: start the copies of `n` Gaussians beginning at `first` into staging buffer `sb`.
+__device__ __forceinline__ void prj_issue(unsigned char *sb, unsigned bar, size_t first, int n, const float *means3D,
+					  const float *scales, const float *rotations, const float *cov3D_precomp,
+					  const float *opacities, const float *colors)
+{
+	const float *p_xyz = means3D + 3 * first;
+	const float *p_sc = cov3D_precomp ? cov3D_precomp + 6 * first : scales + 3 * first;
+	const float *p_rot = cov3D_precomp ? nullptr : rotations + 4 * first;
+	const float *p_opa = opacities ? opacities + first : nullptr;
+	const float *p_col = colors ? colors + 2 * first : nullptr;
+	const int e_sc = cov3D_precomp ? 24 : 12;
+	unsigned total = 0;
+	// < 16 B tail of a partial tile: plain stores, ordered before the arrive below
+	auto tail = [&](const float *src, int offb, int elt) {
+		if (!src) return;
+		const int nb = n * elt, nb16 = nb & ~15;
+		total += (unsigned)nb16;
+		for (int b = nb16; b < nb; b += 4)
+			*reinterpret_cast<float *>(sb + offb + b) = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(src) + b);
+	};
+	tail(p_xyz, PrjStage::XYZ, 12); tail(p_sc, PrjStage::SC, e_sc); tail(p_rot, PrjStage::ROT, 16);
+	tail(p_opa, PrjStage::OPA, 4); tail(p_col, PrjStage::COL, 8);
+	lgs_mbar_arrive_expect_tx(bar, total); // release: the tail stores above are visible to whoever sees the phase complete
+	auto bulk = [&](const float *src, int offb, int elt) {
+		if (!src) return;
+		const int nb16 = (n * elt) & ~15;
+		if (nb16) lgs_bulk_g2s(lgs_smem_addr(sb + offb), src, (unsigned)nb16, bar);
+	};
+	bulk(p_xyz, PrjStage::XYZ, 12); bulk(p_sc, PrjStage::SC, e_sc); bulk(p_rot, PrjStage::ROT, 16);
+	bulk(p_opa, PrjStage::OPA, 4); bulk(p_col, PrjStage::COL, 8);
+}
+// use_tma = 0: the same staging layout filled by all threads with coalesced loads
+__device__ __forceinline__ void prj_coop_fill(unsigned char *sb, size_t first, int n, const float *means3D, const float *scales,
+					      const float *rotations, const float *cov3D_precomp, const float *opacities,
+					      const float *colors)
+{
+	auto fill = [&](const float *src, int offb, int words) {
+		float *dst = reinterpret_cast<float *>(sb + offb);
+		for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+	};
+	fill(means3D + 3 * first, PrjStage::XYZ, 3 * n);
+	if (cov3D_precomp) fill(cov3D_precomp + 6 * first, PrjStage::SC, 6 * n);
+	else { fill(scales + 3 * first, PrjStage::SC, 3 * n); fill(rotations + 4 * first, PrjStage::ROT, 4 * n); }
+	if (opacities) fill(opacities + first, PrjStage::OPA, n);
+	if (colors) fill(colors + 2 * first, PrjStage::COL, 2 * n);
+}
+
+template <bool FILTER>
+__global__ void __launch_bounds__(PRJ_TILE, 4)
+project_kernel(int P, int use_tma, const float *__restrict__ means3D, const float *__restrict__ scales, float mod,
 	       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
 	       const float *__restrict__ opacities, const float *__restrict__ colors,
 	       const float *__restrict__ view, int W, int H, const float *__restrict__ beams,
 	       int far_, int near_, int gx, int RB,
 	       float4 *__restrict__ rec, uint4 *__restrict__ aux, int *__restrict__ radii,
-	       int *__restrict__ radii_xy, uint32_t *__restrict__ cnt, FrameTotals *__restrict__ totals)
+	       int *__restrict__ radii_xy, uint32_t *__restrict__ cnt, uint32_t *__restrict__ ranks, unsigned capacity,
+	       FrameTotals *__restrict__ totals)
 {
-	extern __shared__ float stab[];
+	extern __shared__ __align__(128) unsigned char psm[];
+	const unsigned bar0 = lgs_smem_addr(psm);
+	unsigned char *stage0 = psm + PRJ_HDR;
+	float *stab = reinterpret_cast<float *>(stage0 + PRJ_STAGES * PrjStage::BYTES);
+	const int tid = threadIdx.x;
+	const int ntiles = (P + PRJ_TILE - 1) / PRJ_TILE;
+	if (tid == 0 && use_tma) {
+#pragma unroll
+		for (int s = 0; s < PRJ_STAGES; s++) lgs_mbar_init(bar0 + 8 * s, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (tid == 0 && use_tma) {
+#pragma unroll
+		for (int s = 0; s < PRJ_STAGES; s++) {
+			const int t = blockIdx.x + s * gridDim.x;
+			if (t < ntiles)
+				prj_issue(stage0 + s * PrjStage::BYTES, bar0 + 8 * s, (size_t)t * PRJ_TILE, min(PRJ_TILE, P - t * PRJ_TILE),
+					  means3D, scales, rotations, cov3D_precomp, opacities, colors);
+		}
+	}
 	const float *bt, *tt;
 	float tanW;
-	load_beam_tables(beams, H, W, stab, stab + H, bt, tt, tanW);
-	int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	unsigned tiles = 0, vis = 0;
-	int cx0 = 0, cnx = 1, cg0 = 0, cn = 0, cbucket = 0; // (bin, bucket) instances of this Gaussian to count
-	if (idx < P) {
-		// issue the loads that are only needed at the end now, so their latency hides behind the projection math
-		const float o = opacities[idx];
-		const float2 f = *reinterpret_cast<const float2 *>(colors + 2 * (size_t)idx);
+	load_beam_tables(beams, H, W, stab, stab + H, bt, tt, tanW); // (ends with a CTA barrier when the tables fit)
+
+	unsigned long long t64 = 0; // block-level totals, flushed once per CTA
+	unsigned vis = 0;
+	int it = 0;
+	for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+		const int s = it % PRJ_STAGES;
+		unsigned char *sb = stage0 + s * PrjStage::BYTES;
+		const size_t first = (size_t)tile * PRJ_TILE;
+		const int n = min(PRJ_TILE, P - tile * PRJ_TILE);
+		if (use_tma) lgs_mbar_wait(bar0 + 8 * s, (unsigned)(it / PRJ_STAGES) & 1u);
+		else {
+			prj_coop_fill(sb, first, n, means3D, scales, rotations, cov3D_precomp, opacities, colors);
+			__syncthreads();
+		}
+		// ---- this thread's Gaussian: shared memory -> registers ----
+		const bool have = tid < n;
+		const int idx = (int)first + tid;
+		float px = 0.f, py = 0.f, pz = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, o = 0.f;
+		float4 rq = make_float4(0.f, 0.f, 0.f, 0.f);
+		float2 f = make_float2(0.f, 0.f);
+		float cov[6];
+		if (have) {
+			const float *sx = reinterpret_cast<const float *>(sb + PrjStage::XYZ) + 3 * tid;
+			px = sx[0]; py = sx[1]; pz = sx[2];
+			if (cov3D_precomp) {
+				const float2 *sc = reinterpret_cast<const float2 *>(sb + PrjStage::SC) + 3 * tid;
+				const float2 c0 = sc[0], c1 = sc[1], c2 = sc[2];
+				cov[0] = c0.x; cov[1] = c0.y; cov[2] = c1.x; cov[3] = c1.y; cov[4] = c2.x; cov[5] = c2.y;
+			} else {
+				const float *ss = reinterpret_cast<const float *>(sb + PrjStage::SC) + 3 * tid;
+				s0 = ss[0]; s1 = ss[1]; s2 = ss[2];
+				rq = reinterpret_cast<const float4 *>(sb + PrjStage::ROT)[tid];
+			}
+			if (!FILTER) {
+				o = reinterpret_cast<const float *>(sb + PrjStage::OPA)[tid];
+				f = reinterpret_cast<const float2 *>(sb + PrjStage::COL)[tid];
+			}
+		}
+		__syncthreads(); // every thread has read its inputs: the buffer can take the tile after next
+		if (tid == 0 && use_tma) {
+			const int t = tile + PRJ_STAGES * gridDim.x;
+			if (t < ntiles)
+				prj_issue(sb, bar0 + 8 * s, (size_t)t * PRJ_TILE, min(PRJ_TILE, P - t * PRJ_TILE), means3D, scales, rotations,
+					  cov3D_precomp, opacities, colors);
+		}
+		// ---- project ----
+		int cx0 = 0, cnx = 1, cg0 = 0, cn = 0, cbucket = 0; // (bin, bucket) instances of this Gaussian
 		Projected pj;
-		bool ok = project_gaussian<false>(idx, means3D, scales, mod, rotations, cov3D_precomp, view, W, H, bt, tt, tanW,
-						  far_, near_, gx, H, pj);
+		bool ok = false;
+		if (have) ok = project_gaussian<FILTER>(px, py, pz, cov3D_precomp ? cov : nullptr, s0, s1, s2, mod, rq, view, W, H, bt, tt,
+							tanW, far_, near_, gx, H, pj);
+		if (FILTER) {
+			if (have) {
+				radii[idx] = ok ? max(pj.rx, pj.ry) : 0;
+				if (radii_xy) {
+					radii_xy[2 * idx] = ok ? pj.rx : 0;
+					radii_xy[2 * idx + 1] = ok ? pj.ry : 0;
+				}
+			}
+			continue;
+		}
 		if (ok) {
 			float4 *r = rec + 4 * (size_t)idx;
 			r[0] = make_float4(pj.conic.x, pj.conic.y, pj.conic.z, o);
 			r[1] = make_float4(pj.s.x, pj.s.y, pj.s.z, pj.depth);
 			r[2] = make_float4(pj.u1.x, pj.u1.y, pj.u1.z, f.x);
 			r[3] = make_float4(pj.u2.x, pj.u2.y, pj.u2.z, f.y);
-			int bucket = depth_bucket(pj.depth, far_, near_);
-			aux[idx] = make_uint4((unsigned)pj.x0 | ((unsigned)pj.x1 << 16), (unsigned)pj.y0 | ((unsigned)pj.y1 << 16),
-					      __float_as_uint(pj.depth), (unsigned)bucket);
 			radii[idx] = max(pj.rx, pj.ry);
 			if (radii_xy) {
 				radii_xy[2 * idx] = pj.rx;
 				radii_xy[2 * idx + 1] = pj.ry;
 			}
-			tiles = (unsigned)((pj.x1 - pj.x0) * (pj.y1 - pj.y0));
-			vis = 1;
+			t64 += (unsigned)((pj.x1 - pj.x0) * (pj.y1 - pj.y0));
+			vis += 1;
 			cx0 = pj.x0; cnx = pj.x1 - pj.x0; cg0 = pj.y0 / RB;
 			cn = cnx * ((pj.y1 - 1) / RB - cg0 + 1);
-			cbucket = bucket;
-		} else {
-			aux[idx] = make_uint4(0, 0, 0, 0);
+			cbucket = lgs_depth_bucket(pj.depth, far_, near_);
+		} else if (have) {
 			radii[idx] = 0;
 			if (radii_xy) {
 				radii_xy[2 * idx] = 0;
 				radii_xy[2 * idx + 1] = 0;
 			}
 		}
+		// count the (bin, depth bucket) instances and file their ranks (see lgs_emit_instances)
+		const unsigned soff = lgs_emit_instances(cx0, cnx, cg0, cn, cbucket, gx, cnt, ranks, capacity, &totals->rank_cursor);
+		if (have)
+			aux[idx] = ok ? make_uint4((unsigned)pj.x0 | ((unsigned)pj.x1 << 16), (unsigned)pj.y0 | ((unsigned)pj.y1 << 16),
+						   __float_as_uint(pj.depth), soff)
+				      : make_uint4(0, 0, 0, 0);
 	}
-	// count the (bin, depth bucket) instances; large footprints are expanded by the whole warp
-	{
-		const int lane = threadIdx.x & 31;
-		if (cn < 12) {
-			for (int i = 0; i < cn; i++)
-				atomicAdd(&cnt[(size_t)((cg0 + i / cnx) * gx + cx0 + i % cnx) * LGS_NB + cbucket], 1u);
-		}
-		unsigned big = __ballot_sync(0xffffffffu, cn >= 12);
-		while (big) {
-			const int src = __ffs(big) - 1;
-			big &= big - 1;
-			const int sx0 = __shfl_sync(0xffffffffu, cx0, src), snx = __shfl_sync(0xffffffffu, cnx, src);
-			const int sg0 = __shfl_sync(0xffffffffu, cg0, src), sn = __shfl_sync(0xffffffffu, cn, src);
-			const int sb = __shfl_sync(0xffffffffu, cbucket, src);
-			for (int i = lane; i < sn; i += 32)
-				atomicAdd(&cnt[(size_t)((sg0 + i / snx) * gx + sx0 + i % snx) * LGS_NB + sb], 1u);
-		}
-	}
-	// block-level totals: one atomic per warp
-	unsigned long long t64 = tiles;
+	if constexpr (!FILTER) { // totals: one atomic pair per warp and CTA lifetime
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		t64 += __shfl_xor_sync(0xffffffffu, t64, o);
-		vis += __shfl_xor_sync(0xffffffffu, vis, o);
-	}
-	if ((threadIdx.x & 31) == 0 && vis) {
-		atomicAdd(&totals->num_rendered, t64);
-		atomicAdd(&totals->num_visible, vis);
-	}
-}
-
-__global__ void __launch_bounds__(256)
-filter_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ scales, float mod,
-	      const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
-	      const float *__restrict__ view, int W, int H, const float *__restrict__ beams, int far_, int near_,
-	      int gx, int *__restrict__ radii, int *__restrict__ radii_xy)
-{
-	extern __shared__ float stab[];
-	const float *bt, *tt;
-	float tanW;
-	load_beam_tables(beams, H, W, stab, stab + H, bt, tt, tanW);
-	int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= P) return;
-	Projected pj;
-	bool ok = project_gaussian<true>(idx, means3D, scales, mod, rotations, cov3D_precomp, view, W, H, bt, tt, tanW, far_,
-					 near_, gx, H, pj);
-	radii[idx] = ok ? max(pj.rx, pj.ry) : 0;
-	if (radii_xy) {
-		radii_xy[2 * idx] = ok ? pj.rx : 0;
-		radii_xy[2 * idx + 1] = ok ? pj.ry : 0;
+		for (int o = 16; o > 0; o >>= 1) {
+			t64 += __shfl_xor_sync(0xffffffffu, t64, o);
+			vis += __shfl_xor_sync(0xffffffffu, vis, o);
+		}
+		if ((tid & 31) == 0 && vis) {
+			atomicAdd(&totals->num_rendered, t64);
+			atomicAdd(&totals->num_visible, vis);
+		}
 	}
 }
 
@@ -301,15 +391,35 @@ mark_visible_kernel(int P, const float *__restrict__ pts, const float *__restric
 
 } // namespace
 
+namespace {
+inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t prj_smem(int H) { return PRJ_HDR + PRJ_STAGES * (size_t)PrjStage::BYTES + (H <= LGS_MAX_SMEM_ROWS ? 8 * (size_t)H : 0); }
+inline int prj_grid(int P)
+{
+	static int sms = 0;
+	if (!sms) {
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (sms <= 0) sms = 148;
+	}
+	const int ntiles = (P + PRJ_TILE - 1) / PRJ_TILE;
+	return ntiles < 4 * sms ? ntiles : 4 * sms; // persistent: four resident CTAs per SM walk the tiles
+}
+} // namespace
+
 void lgs_launch_project(const FrameGeom &g, const float *means3D, const float *scales, float mod,
 			const float *rotations, const float *cov3D_precomp, const float *opacities,
 			const float *colors, const float *view, const float *beams, int far_, int near_,
-			const GeomPtrs &gp, int *radii, int *radii_xy, cudaStream_t st)
+			const GeomPtrs &gp, int *radii, int *radii_xy, uint32_t *ranks, unsigned capacity, cudaStream_t st)
 {
-	const size_t tab = g.H <= LGS_MAX_SMEM_ROWS ? 8 * (size_t)g.H : 0;
-	project_kernel<<<(g.P + 255) / 256, 256, tab, st>>>(g.P, means3D, scales, mod, rotations, cov3D_precomp, opacities,
-							  colors, view, g.W, g.H, beams, far_, near_, g.gx, g.RB, gp.rec,
-							  gp.aux, radii, radii_xy, gp.cnt, gp.totals);
+	const int use_tma = al16(means3D) && al16(opacities) && al16(colors) &&
+			    (cov3D_precomp ? al16(cov3D_precomp) : (al16(scales) && al16(rotations)));
+	const size_t smem = prj_smem(g.H);
+	cudaFuncSetAttribute(project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	project_kernel<false><<<prj_grid(g.P), PRJ_TILE, smem, st>>>(g.P, use_tma, means3D, scales, mod, rotations, cov3D_precomp,
+								     opacities, colors, view, g.W, g.H, beams, far_, near_, g.gx, g.RB,
+								     gp.rec, gp.aux, radii, radii_xy, gp.cnt, ranks, capacity, gp.totals);
 }
 
 void lgs_launch_filter(int P, const float *means3D, const float *scales, float mod, const float *rotations,
@@ -317,9 +427,12 @@ void lgs_launch_filter(int P, const float *means3D, const float *scales, float m
 		       int near_, int *radii, int *radii_xy, cudaStream_t st)
 {
 	int gx = (W + LGS_TILE_X_ - 1) / LGS_TILE_X_;
-	const size_t tab = H <= LGS_MAX_SMEM_ROWS ? 8 * (size_t)H : 0;
-	filter_kernel<<<(P + 255) / 256, 256, tab, st>>>(P, means3D, scales, mod, rotations, cov3D_precomp, view, W, H, beams,
-						       far_, near_, gx, radii, radii_xy);
+	const int use_tma = al16(means3D) && (cov3D_precomp ? al16(cov3D_precomp) : (al16(scales) && al16(rotations)));
+	const size_t smem = prj_smem(H);
+	cudaFuncSetAttribute(project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	project_kernel<true><<<prj_grid(P), PRJ_TILE, smem, st>>>(P, use_tma, means3D, scales, mod, rotations, cov3D_precomp, nullptr,
+								  nullptr, view, W, H, beams, far_, near_, gx, 1, nullptr, nullptr, radii,
+								  radii_xy, nullptr, nullptr, 0u, nullptr);
 }
 
 void lgs_launch_mark_visible(int P, const float *means3D, const float *view, unsigned char *present, cudaStream_t st)

@@ -164,8 +164,9 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 		  const float *__restrict__ bg, const float *__restrict__ beams,
 		  float *__restrict__ final_T, uint32_t *__restrict__ n_contrib, uint32_t *__restrict__ sorted_end,
 		  float4 *__restrict__ fin, uint4 *__restrict__ cta_prof, float *__restrict__ out_color,
-		  float *__restrict__ out_depth, float *__restrict__ out_occ, int sort_all)
+		  float *__restrict__ out_depth, float *__restrict__ out_occ, int sort_all, const FrameTotals *__restrict__ totals)
 {
+	if (totals->overflow) return; // binning buffer too small for this frame: the host re-runs it (lgs_abi.cu)
 	using C = FwdCfg<RB>;
 	const long long clk0 = clock64();
 	const unsigned t0us = lgs_globaltimer_us();
@@ -434,7 +435,7 @@ void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uin
 	cudaFuncSetAttribute(render_fwd_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
 	render_fwd_kernel<RB><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, gp.order, entries, bg, beams,
 								 ip.final_T, ip.n_contrib, ip.sorted_end, ip.fin, ip.cta_prof, out_color,
-								 out_depth, out_occ, sort_all);
+								 out_depth, out_occ, sort_all, gp.totals);
 }
 
 } // namespace

@@ -142,22 +142,17 @@ __device__ __forceinline__ bool project_surfel(int idx, const float *__restrict_
 	return true;
 }
 
-__device__ __forceinline__ int s_depth_bucket(float depth, int far_, int near_)
-{
-	float t = (depth - (float)near_) * ((float)LGS_NB / (float)(far_ - near_));
-	return min(LGS_NB - 1, max(0, (int)t));
-}
-
 __global__ void __launch_bounds__(256)
 surfel_project_kernel(int P, const float *__restrict__ means, const float *__restrict__ scales, float mod,
 		      const float *__restrict__ rots, const float *__restrict__ opac, const float *__restrict__ colors,
 		      const float *__restrict__ view, int W, int H, const float *__restrict__ beams, int far_, int near_, int gx,
 		      int RB, float4 *__restrict__ rec, uint4 *__restrict__ aux, int *__restrict__ radii, int *__restrict__ radii_xy,
-		      uint32_t *__restrict__ cnt, FrameTotals *__restrict__ totals)
+		      uint32_t *__restrict__ cnt, uint32_t *__restrict__ ranks, unsigned capacity, FrameTotals *__restrict__ totals)
 {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	unsigned tiles = 0, vis = 0;
 	int cx0 = 0, cnx = 1, cg0 = 0, cn = 0, cbucket = 0;
+	uint4 ax = make_uint4(0, 0, 0, 0);
 	if (idx < P) {
 		const float o = opac[idx];
 		const float2 ft = *reinterpret_cast<const float2 *>(colors + 2 * (size_t)idx);
@@ -171,9 +166,9 @@ surfel_project_kernel(int P, const float *__restrict__ means, const float *__res
 			r[2] = make_float4(f.Tv[0], f.Tv[1], f.Tv[2], lgs_dot_self(f.Tv[0], f.Tv[1], f.Tv[2]));
 			r[3] = make_float4(f.Tw[0], f.Tw[1], f.Tw[2], f.dist); // |Tw|: same expression as dist (fwd.cu:438 vs :260)
 			r[4] = make_float4(pj.pix.x, pj.pix.y, ft.x, ft.y);
-			const int bucket = s_depth_bucket(f.dist, far_, near_);
-			aux[idx] = make_uint4((unsigned)pj.x0 | ((unsigned)pj.x1 << 16), (unsigned)pj.y0 | ((unsigned)pj.y1 << 16),
-					      __float_as_uint(f.dist), (unsigned)bucket);
+			const int bucket = lgs_depth_bucket(f.dist, far_, near_);
+			ax = make_uint4((unsigned)pj.x0 | ((unsigned)pj.x1 << 16), (unsigned)pj.y0 | ((unsigned)pj.y1 << 16),
+					__float_as_uint(f.dist), 0u);
 			radii[idx] = max(pj.rx, pj.ry);
 			if (radii_xy) { radii_xy[2 * idx] = pj.rx; radii_xy[2 * idx + 1] = pj.ry; }
 			tiles = (unsigned)((pj.x1 - pj.x0) * (pj.y1 - pj.y0));
@@ -182,26 +177,13 @@ surfel_project_kernel(int P, const float *__restrict__ means, const float *__res
 			cn = cnx * ((pj.y1 - 1) / RB - cg0 + 1);
 			cbucket = bucket;
 		} else {
-			aux[idx] = make_uint4(0, 0, 0, 0);
 			radii[idx] = 0;
 			if (radii_xy) { radii_xy[2 * idx] = 0; radii_xy[2 * idx + 1] = 0; }
 		}
 	}
-	{ // (bin, depth bucket) instance counts; large footprints are expanded by the whole warp
-		const int lane = threadIdx.x & 31;
-		if (cn < 12) {
-			for (int i = 0; i < cn; i++) atomicAdd(&cnt[(size_t)((cg0 + i / cnx) * gx + cx0 + i % cnx) * LGS_NB + cbucket], 1u);
-		}
-		unsigned big = __ballot_sync(0xffffffffu, cn >= 12);
-		while (big) {
-			const int src = __ffs(big) - 1;
-			big &= big - 1;
-			const int sx0 = __shfl_sync(0xffffffffu, cx0, src), snx = __shfl_sync(0xffffffffu, cnx, src);
-			const int sg0 = __shfl_sync(0xffffffffu, cg0, src), sn = __shfl_sync(0xffffffffu, cn, src);
-			const int sb = __shfl_sync(0xffffffffu, cbucket, src);
-			for (int i = lane; i < sn; i += 32) atomicAdd(&cnt[(size_t)((sg0 + i / snx) * gx + sx0 + i % snx) * LGS_NB + sb], 1u);
-		}
-	}
+	// (bin, depth bucket) instance counts + their ranks (see lgs_emit_instances in lgs_common.cuh)
+	ax.w = lgs_emit_instances(cx0, cnx, cg0, cn, cbucket, gx, cnt, ranks, capacity, &totals->rank_cursor);
+	if (idx < P) aux[idx] = ax;
 	unsigned long long t64 = tiles;
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) {
@@ -323,11 +305,12 @@ surfel_finalize_bwd_kernel(int P, const float *__restrict__ means, const float *
 
 void lgs_launch_surfel_project(const FrameGeom &g, const float *means3D, const float *scales, float mod, const float *rotations,
 			       const float *opacities, const float *colors, const float *view, const float *beams, int far_,
-			       int near_, const GeomPtrs &gp, int *radii, int *radii_xy, cudaStream_t st)
+			       int near_, const GeomPtrs &gp, int *radii, int *radii_xy, uint32_t *ranks, unsigned capacity,
+			       cudaStream_t st)
 {
 	surfel_project_kernel<<<(g.P + 255) / 256, 256, 0, st>>>(g.P, means3D, scales, mod, rotations, opacities, colors, view, g.W, g.H,
 								  beams, far_, near_, g.gx, g.RB, gp.rec, gp.aux, radii, radii_xy, gp.cnt,
-								  gp.totals);
+								  ranks, capacity, gp.totals);
 }
 
 void lgs_launch_surfel_filter(int P, const float *means3D, const float *scales, float mod, const float *rotations,

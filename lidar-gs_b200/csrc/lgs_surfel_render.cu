@@ -77,8 +77,10 @@ surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 			 const uint32_t *__restrict__ binbase, const uint32_t *__restrict__ order, uint4 *__restrict__ entries,
 			 const float *__restrict__ bg, const float *__restrict__ beams, float *__restrict__ final_T,
 			 uint32_t *__restrict__ n_contrib, uint32_t *__restrict__ sorted_end, float4 *__restrict__ finA,
-			 float4 *__restrict__ finB, float *__restrict__ out_color, float *__restrict__ out_others, int sort_all)
+			 float4 *__restrict__ finB, float *__restrict__ out_color, float *__restrict__ out_others, int sort_all,
+			 const FrameTotals *__restrict__ totals)
 {
+	if (totals->overflow) return; // binning buffer too small for this frame: the host re-runs it (lgs_abi.cu)
 	using C = SFwdCfg<RB>;
 	constexpr int NT = C::NT, NPG = C::NPG, B = SFB, LD = SFLD, LPT = C::LPT, NCH = SFB / 32;
 	extern __shared__ __align__(16) unsigned char smem[];
@@ -687,7 +689,7 @@ void launch_sfwd(const FrameGeom &g, const GeomPtrs &gp, const SurfelImagePtrs &
 	}
 	surfel_render_fwd_kernel<RB><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, gp.order, entries, bg, beams,
 									ip.final_T, ip.n_contrib, ip.sorted_end, ip.finA, ip.finB, out_color,
-									out_others, sort_all);
+									out_others, sort_all, gp.totals);
 }
 
 } // namespace

@@ -251,3 +251,60 @@ def test_sparse_gradient_readback_is_lossless():
     assert found == want and small.shape[0] == 11
     with pytest.raises(RuntimeError):
         dp.pack_nonzero_rows({k: grads[k].cpu() for k in keys}, None, 10)
+
+
+def test_binning_buffer_overflow_reruns_the_frame():
+    """The binning buffer is sized BEFORE the instance count of the frame is known (no host wait in the middle of the
+    frame; the reference blocks on a read-back of num_rendered, rasterizer_impl.cu:292).  A buffer that turns out too
+    small must be detected on the device, the frame re-run with the exact size, and nothing of the first attempt may
+    leak into the result: images, radii, num_rendered, lists and gradients equal those of a comfortably sized run."""
+    from lgs_b200 import capi
+    L = capi.load()
+    sc = _scene(30000, 32, 512, 11, pose="random")
+    L.lgs_set_capacity_hint(0)
+    ref, fr_ref = util.run_abi(sc)
+    N = ref["num_instances"]
+    assert N > 1000
+    for cap in (1, N // 2, N - 1):
+        before = L.lgs_overflow_reruns()
+        L.lgs_set_capacity_hint(int(cap))
+        try:
+            res, fr = util.run_abi(sc)
+        finally:
+            L.lgs_set_capacity_hint(0)
+        assert L.lgs_overflow_reruns() == before + 1, cap
+        assert res["num_rendered"] == ref["num_rendered"] and res["num_instances"] == N
+        assert np.array_equal(res["radii"], ref["radii"])
+        for k in ("color", "depth", "occ"):
+            assert np.array_equal(res[k].view(np.uint32), ref[k].view(np.uint32)), (cap, k)
+        util.assert_grads_close(res["grads"], ref["grads"], tol=1e-5, what=f"cap={cap}")
+    # exactly enough: no re-run
+    before = L.lgs_overflow_reruns()
+    L.lgs_set_capacity_hint(int(N))
+    try:
+        res, _ = util.run_abi(sc)
+    finally:
+        L.lgs_set_capacity_hint(0)
+    assert L.lgs_overflow_reruns() == before
+    assert np.array_equal(res["color"].view(np.uint32), ref["color"].view(np.uint32))
+
+
+def test_high_water_mark_follows_a_growing_scene():
+    """Same shape (P, H, W), footprints five times larger on the second frame: the high-water mark of the first frame
+    is too small, the second frame must still come out right (one re-run), and the third is sized from the second."""
+    from lgs_b200 import capi
+    L = capi.load()
+    small = _scene(20000, 32, 512, 12, pose="identity", scale_range=(0.01, 0.02))
+    big = dict(small)
+    big["scales"] = np.ascontiguousarray(small["scales"] * 8.0)
+    util.run_abi(small)
+    before = L.lgs_overflow_reruns()
+    res_big, _ = util.run_abi(big)
+    reruns = L.lgs_overflow_reruns() - before
+    ref = util.oracle_run(big)
+    assert res_big["num_rendered"] == ref["num_rendered"]
+    util.assert_forward_close(res_big, ref, floor=1e-3, max_outlier_frac=0.005, what="grown scene")
+    before = L.lgs_overflow_reruns()
+    util.run_abi(big)
+    assert L.lgs_overflow_reruns() == before, "third frame must fit the high-water mark of the second"
+    assert reruns in (0, 1)

@@ -19,20 +19,19 @@ img=fr.image
 o=_al(4*H*W); o=_al(o+4*H*W); o=_al(o+4*nb); o=_al(o+16*H*W)
 prof=img[o:o+16*nb].view(torch.int32).view(nb,4).cpu().numpy().astype(np.int64) & 0xffffffff
 se=v["sorted_end"].cpu().numpy()
-t0=prof[:,0]-prof[:,0].min(); dur=prof[:,1]; sm=prof[:,2]; nbat=prof[:,3]&0xffffff; tailf=(prof[:,3]>>31)&1; ntail=(prof[:,3]>>24)&0x7f
-print("CTAs that entered straggler mode:", int(tailf.sum()), "mean live pixels at switch", float(ntail[tailf>0].mean()) if tailf.any() else None)
+t0=prof[:,0]-prof[:,0].min(); dur=prof[:,1]; sm=prof[:,2]; nbat=prof[:,3]  # chunks of 32 (entry, row) pairs evaluated by the workers of the CTA
 print("CTAs",nb,"start us: min/median/max",t0.min(),np.median(t0),t0.max())
 print("duration kcycles: mean %.1f median %.1f p90 %.1f max %.1f"%(dur.mean()/1e3,np.median(dur)/1e3,np.percentile(dur,90)/1e3,dur.max()/1e3))
 idx=np.argsort(-dur)[:12]
-print("heaviest CTAs: (dur kcyc, sorted entries, batches, start us, sm)")
-for i in idx: print("   %.1f %d %d %d %d tail=%d ntail=%d"%(dur[i]/1e3, se[i], nbat[i], t0[i], sm[i], tailf[i], ntail[i]))
+print("heaviest CTAs: (dur kcyc, sorted entries, chunks, start us, sm)")
+for i in idx: print("   %.1f %d %d %d %d"%(dur[i]/1e3, se[i], nbat[i], t0[i], sm[i]))
 # cycles per batch for big vs small
 big=nbat>40; small=(nbat>0)&(nbat<=12)
-print("kcycles per batch: big bins %.2f, small bins %.2f"%((dur[big]/nbat[big]).mean()/1e3,(dur[small]/nbat[small]).mean()/1e3))
+print("kcycles per chunk: big bins %.2f, small bins %.2f"%((dur[big]/nbat[big]).mean()/1e3,(dur[small]/nbat[small]).mean()/1e3))
 # per-SM busy sum
 busy=np.zeros(sm.max()+1); 
 for s_,d_ in zip(sm,dur): busy[s_]+=d_
-print("per-SM sum of CTA durations kcyc: min %.0f mean %.0f max %.0f (CTAs overlap, 2/SM)"%(busy.min()/1e3,busy.mean()/1e3,busy.max()/1e3))
+print("per-SM sum of CTA durations kcyc: min %.0f mean %.0f max %.0f (CTAs overlap, 4/SM)"%(busy.min()/1e3,busy.mean()/1e3,busy.max()/1e3))
 end=t0+dur/1965.0
 print("kernel span us (from CTA timers): %.1f"%(end.max()))
 hist=np.histogram(se,bins=[0,100,200,300,400,600,800,1200,1600,2400])
