@@ -335,6 +335,9 @@ int lgs_adam_step(int ntensors, const lgs_adam_tensor *tensors, void *stream);
 int lgs_set_rows_per_bin(int rows);
 /* 1 = sort every list completely in forward (tests); 0 = sort only what compositing consumes. */
 int lgs_set_sort_all(int on);
+/* 1 = forward compositing as three launches (prefix sort, independent pixel-group warps, tail); 0 = one pipelined
+ * launch (default, faster on every workload measured; the split stays as a tested alternative). */
+int lgs_set_forward_split(int on);
 /* Number of (Gaussian, bin) instances materialised by the last lgs_forward() on this thread. */
 long long lgs_last_num_instances(void);
 /*

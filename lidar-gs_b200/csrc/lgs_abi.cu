@@ -33,6 +33,7 @@ struct DevState {
 thread_local DevState g_dev[LGS_MAX_DEVICES];
 std::atomic<int> g_rows_per_bin{0};
 std::atomic<int> g_sort_all{0};
+std::atomic<int> g_fwd_split{0};
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_capacity_hint{0}; // test knob: forces the capacity guess of the next frames (0 = automatic)
 
@@ -182,7 +183,7 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 		g_timer.begin(LGS_STAGE_RENDER_FWD, st);
 		render(entries);
 		g_timer.end(st);
-		g_launches += 5;
+		g_launches += g_fwd_split.load() && path == 0 ? 7 : 5; // project, 2 x scan, scatter, compositing (1 or 3 launches)
 		CK(cudaGetLastError());
 		// the scan kernel stored the totals straight into mapped host memory (a memcpy would queue behind whatever bulk
 		// device-to-host transfer the application has in flight on the copy engine); scatter + render keep running
@@ -256,7 +257,7 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn 
 		},
 		[&](uint4 *entries) {
 			lgs_launch_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_depth, out_occ,
-					      g_sort_all.load(), st);
+					      g_sort_all.load(), g_fwd_split.load(), st);
 		},
 		&R);
 	if (rc < 0) return rc;
@@ -519,6 +520,11 @@ int lgs_set_rows_per_bin(int rows)
 int lgs_set_sort_all(int on)
 {
 	g_sort_all.store(on ? 1 : 0);
+	return 0;
+}
+int lgs_set_forward_split(int on)
+{
+	g_fwd_split.store(on ? 1 : 0);
 	return 0;
 }
 int lgs_timing_enable(int on)

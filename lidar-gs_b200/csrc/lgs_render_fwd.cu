@@ -1,19 +1,31 @@
 // lgs_render_fwd.cu -- lazy per-bin depth sort fused with front-to-back compositing.
 //
 // Restates R3 forward.cu:503-641 (renderCUDA) and the per-tile ordering that the reference gets from
-// cub::DeviceRadixSortPairs on tile|depth keys (rasterizer_impl.cu:317-322).  One CTA owns one bin
-// (16 columns x RB rows of pixels) and is made of independent warps that never meet at a CTA barrier:
+// cub::DeviceRadixSortPairs on tile|depth keys (rasterizer_impl.cu:317-322).  A bin is 16 columns x RB rows of
+// pixels; its list is bucketed by depth (lgs_bin.cu) and sorted LAZILY, front to back, only as far as the bin's
+// rays travel before the reference's T < 1e-4 stop.  No kernel here has a CTA-wide barrier in its loop.  By default the
+// whole pass is ONE launch of kernel C in "full" mode (every bin starts from scratch); with lgs_set_forward_split(1) a
+// fixed prefix is sorted and composited by fully independent warps first (A, B) and C only continues the bins whose
+// rays outlive the prefix.  Measured on cfg3 (B200): one kernel 0.118 ms, split 0.178 ms -- B alone costs as much as
+// the one-kernel pass (both are bound by instruction issue, ~55 M warp instructions), and the few heavy bins C is left
+// with then run by themselves instead of alongside everything else.
 //
-//   sorter warp   walks the bin's depth buckets front to back.  Consecutive buckets are grouped into segments;
-//                 a segment is sorted on (depth bits, Gaussian idx) -- the tie-break a stable LSD sort over
-//                 idx-ordered input gives -- with a counting sort on the quantised depth followed by a rank
-//                 inside each sub-bucket, written back in place (the backward pass replays it) and published
-//                 to the workers through a two-slot ring guarded by mbarriers (full / empty).  It stops as soon
-//                 as every pixel of the bin has hit the reference's T < 1e-4 stop: buckets behind the stop are
-//                 never read, sorted or gathered.
-//   worker warps  one per 32-pixel group (2 rows x 16 columns).  A worker scans a published segment (lanes =
-//                 entries), keeps the (entry, row) PAIRS whose rect covers one of its two rows and whose row
-//                 still has live pixels, and queues them.  Every 32 queued pairs form a chunk:
+//   A  sort_prefix_kernel      one warp per bin sorts the first ~FWD_PREFIX entries of the list: whole depth buckets,
+//                              grouped into segments that travel to shared memory as one bulk copy (TMA) each, issued
+//                              one segment ahead; counting sort on the quantised depth + rank inside each sub-bucket
+//                              on (depth bits, Gaussian idx) -- the tie-break a stable LSD sort over idx-ordered input
+//                              gives; written back in place (the backward pass replays the sorted prefix).
+//   B  render_fwd_groups_kernel one warp per (bin, 32-pixel group = 2 rows x 16 columns), independent of every other
+//                              warp, composites the sorted prefix.  Most rays saturate inside it.
+//   C  render_fwd_tail_kernel  one CTA per bin that B left unfinished (rays still alive at the end of the sorted
+//                              prefix): a sorter warp keeps sorting segments and publishes them through a two-slot
+//                              ring guarded by mbarriers (full / empty), one worker warp per pixel group resumes
+//                              from the state B saved.  It stops sorting as soon as every pixel of the bin has
+//                              terminated: buckets behind the stop are never read, sorted or gathered.
+//
+// A worker (B and C share the code: GroupWorker) scans sorted entries (lanes = entries), keeps the (entry, row) PAIRS
+// whose rect covers one of its two rows and whose row still has live pixels, and queues them.  Every 32 queued pairs
+// form a chunk:
 //       evaluate : LANES ARE PAIRS, the loop runs over the live pixels of the pair's row: the 64-B record
 //                  (prefetched into registers one chunk ahead) never leaves the lane, the pixel's ray is a
 //                  shared-memory broadcast, terminated pixels cost nothing.  Non-zero alphas go to a
@@ -27,38 +39,47 @@
 
 namespace {
 
-#define FWD_CAP 512      // entries per published segment slot (a single depth bucket larger than this is "oversized")
-#define FWD_TARGET 256   // buckets are grouped until a segment has at least this many entries
+#define FWD_CAP 512      // entries per segment (a single depth bucket larger than this is "oversized")
+#define FWD_TARGET 128   // buckets are grouped until a segment has at least this many entries
+#define FWD_PREFIX 512   // kernel A sorts whole segments until at least this many entries of the bin are sorted
 #define FWD_NSUB 256     // sub-buckets of the counting sort
-#define FWD_NSLOT 2      // ring depth: how far the sorter may run ahead of the slowest worker
+#define FWD_NSLOT 2      // kernel C's ring depth: how far the sorter may run ahead of the slowest worker
 #define FWD_QCAP 128     // pair queue ring (needs 31 + 64)
 #define FWD_TLD 33       // alpha tile row stride (floats): conflict-free for lanes = pairs stores
+#define FWD_PER (FWD_CAP / 32) // entries per sorter lane
+#define FWD_GW 4         // kernels A and B: independent warps per CTA
 
-template <int RB> struct FwdCfg {
+// shared memory of one worker warp (bytes)
+struct WorkSmem {
+	static constexpr size_t TILE = 0;                          // float [16 columns][FWD_TLD]: a pair belongs to ONE row, so pixel
+	                                                           // (row, column) only reads tile[column][pair] of its own row's pairs
+	static constexpr size_t PF = TILE + 4 * 16 * FWD_TLD;      // float4 per pair: feature0, feature1, depth, list position
+	static constexpr size_t RAY = PF + 16 * 32;                // float4 per pixel, index column * 2 + row
+	static constexpr size_t PMASK = RAY + 16 * 32;             // u32 per pixel (index row * 16 + column)
+	static constexpr size_t QUEUE = PMASK + 4 * 32;            // uint2 (id, list position << 1 | row) ring
+	static constexpr size_t BYTES = QUEUE + 8 * FWD_QCAP;
+};
+// shared memory of one sorter warp (bytes)
+struct SortSmem {
+	static constexpr size_t BAR = 0;                           // 2 mbarriers: landing buffers
+	static constexpr size_t LOC = 16;                          // bucket offsets of the bin (LGS_NB + 1)
+	static constexpr size_t RAW = (LOC + 4 * (LGS_NB + 1) + 15) / 16 * 16; // 2 x uint4 [CAP] landing buffers of the bulk copies
+	static constexpr size_t BKEY = RAW + 2 * 16 * FWD_CAP;     // sub-bucketed keys / values
+	static constexpr size_t BVAL = BKEY + 8 * FWD_CAP;
+	static constexpr size_t HIST = BVAL + 4 * FWD_CAP;         // NSUB + 1 counters -> sub-bucket starts
+	static constexpr size_t BYTES = (HIST + 4 * (FWD_NSUB + 1) + 15) / 16 * 16;
+};
+template <int RB> struct TailCfg {
 	static constexpr int NPG = RB >= 2 ? RB / 2 : 1;     // 32-pixel groups (2 rows x 16 columns) = worker warps
 	static constexpr int NW = NPG + 1;                    // + the sorter warp (last)
 	static constexpr int NT = NW * 32;
-	// shared memory carve-up (bytes)
 	static constexpr size_t O_BAR = 0;                                   // full[NSLOT], empty[NSLOT] mbarriers
-	static constexpr size_t O_CTL = O_BAR + 8 * 2 * FWD_NSLOT;           // sdone, sfin
+	static constexpr size_t O_CTL = O_BAR + 8 * 2 * FWD_NSLOT;           // groups done, warps finished, chunks
 	static constexpr size_t O_DESC = O_CTL + 16;                         // uint4 per slot: {list position, count, end, -}
-	static constexpr size_t O_LOC = O_DESC + 16 * FWD_NSLOT;             // bucket offsets of the bin
-	static constexpr size_t O_SLOT = (O_LOC + 4 * (LGS_NB + 1) + 15) / 16 * 16; // uint2 (id, y0 | y1 << 16) per sorted entry
-	static constexpr size_t O_AKEY = O_SLOT + 8 * FWD_CAP * FWD_NSLOT;   // sorter scratch: raw keys / values, sub-bucketed keys / values
-	static constexpr size_t O_BKEY = O_AKEY + 8 * FWD_CAP;
-	static constexpr size_t O_AVAL = O_BKEY + 8 * FWD_CAP;
-	static constexpr size_t O_BVAL = O_AVAL + 4 * FWD_CAP;
-	static constexpr size_t O_HIST = O_BVAL + 4 * FWD_CAP;
-	static constexpr size_t O_WORK = O_HIST + 4 * FWD_NSUB;
-	// per worker
-	static constexpr size_t W_TILE = 0;                                  // float [16 columns][FWD_TLD]: a pair belongs to ONE row, so
-	                                                                     // pixel (row, column) only reads tile[column][pair] of its own row's pairs
-	static constexpr size_t W_PF = W_TILE + 4 * 16 * FWD_TLD;            // float4 per pair: feature0, feature1, depth, list position
-	static constexpr size_t W_RAY = W_PF + 16 * 32;                      // float4 per pixel, index column * 2 + row
-	static constexpr size_t W_PMASK = W_RAY + 16 * 32;                   // u32 per pixel (index row * 16 + column)
-	static constexpr size_t W_QUEUE = W_PMASK + 4 * 32;                  // uint2 (id, list position << 1 | row) ring
-	static constexpr size_t W_BYTES = W_QUEUE + 8 * FWD_QCAP;
-	static constexpr size_t BYTES = O_WORK + NPG * W_BYTES;
+	static constexpr size_t O_SLOT = O_DESC + 16 * FWD_NSLOT;            // uint2 (id, y0 | y1 << 16) per sorted entry
+	static constexpr size_t O_SORT = O_SLOT + 8 * FWD_CAP * FWD_NSLOT;   // SortSmem
+	static constexpr size_t O_WORK = O_SORT + SortSmem::BYTES;           // NPG x WorkSmem
+	static constexpr size_t BYTES = O_WORK + NPG * WorkSmem::BYTES;
 };
 
 __device__ __forceinline__ unsigned warp_excl_scan_u32(unsigned v, int lane)
@@ -102,32 +123,49 @@ __device__ void warp_bitonic_sort_global(uint4 *e, int n, int lane)
 	}
 }
 
-// Sort m <= FWD_CAP entries of `seg` on (depth bits << 32 | idx) with one warp: counting sort on a monotone
-// quantisation of the depth bits (FWD_NSUB sub-buckets over the segment's own range), then rank inside the
-// sub-bucket by the full key (keys are unique: the Gaussian index is part of the key).  The sorted entries
-// are written back to `seg` (spare word = 0: the workers OR their blended-row flags into it) and, as
-// (idx, y-range), to the ring slot `so`.
-__device__ __forceinline__ void warp_sort_segment(uint4 *seg, int m, uint2 *so, unsigned long long *akey,
-						  unsigned long long *bkey, unsigned *aval, unsigned *bval, unsigned *hist, int lane)
+// Sort the m <= FWD_CAP entries of a segment, already in shared memory (`raw`, landed there by a bulk copy), on
+// (depth bits << 32 | idx) with one warp: counting sort on a monotone quantisation of the depth bits (FWD_NSUB
+// sub-buckets over the segment's own range), then rank inside the sub-bucket by the full key (keys are unique: the
+// Gaussian index is part of the key).  Every pass is unrolled over the lane's FWD_PER entries so that its shared-memory
+// loads and atomics are in flight together; the sub-bucket and the rank the counting atomic returned stay in registers.
+// The sorted entries are written back to `seg` in global memory (spare word = 0: the workers OR their blended-row flags
+// into it; the backward pass replays them) and, when SLOT, as (idx, y-range) to the ring slot `so`.
+template <bool SLOT>
+__device__ __forceinline__ void warp_sort_segment(uint4 *seg, const uint4 *raw, int m, uint2 *so, unsigned long long *bkey,
+						  unsigned *bval, unsigned *hist, int lane)
 {
 	unsigned dmin = 0xffffffffu, dmax = 0u;
-	for (int i = lane; i < m; i += 32) {
-		const uint4 e = seg[i];
-		akey[i] = ((unsigned long long)e.x << 32) | e.y;
-		aval[i] = e.z;
-		dmin = min(dmin, e.x);
-		dmax = max(dmax, e.x);
+#pragma unroll
+	for (int t = 0; t < FWD_PER; t++) {
+		if (32 * t >= m) break;
+		const int i = lane + 32 * t;
+		if (i < m) {
+			const unsigned d = raw[i].x;
+			dmin = min(dmin, d);
+			dmax = max(dmax, d);
+		}
 	}
 	dmin = __reduce_min_sync(0xffffffffu, dmin);
 	dmax = __reduce_max_sync(0xffffffffu, dmax);
-	for (int i = lane; i < FWD_NSUB; i += 32) hist[i] = 0;
+#pragma unroll
+	for (int t = 0; t < (FWD_NSUB + 32) / 32; t++)
+		if (lane + 32 * t <= FWD_NSUB) hist[lane + 32 * t] = 0;
 	__syncwarp();
 	const float scale = (float)FWD_NSUB / ((float)(dmax - dmin) + 1.0f);
 	// monotone in d: int -> float rounding, a positive scale and truncation all preserve order
 	auto subof = [&](unsigned d) { return min((int)((float)(d - dmin) * scale), FWD_NSUB - 1); };
-	for (int i = lane; i < m; i += 32) atomicAdd(&hist[subof((unsigned)(akey[i] >> 32))], 1u);
+	unsigned code[FWD_PER]; // sub-bucket | rank inside it << 16 (arrival order)
+#pragma unroll
+	for (int t = 0; t < FWD_PER; t++) {
+		if (32 * t >= m) break;
+		const int i = lane + 32 * t;
+		if (i < m) {
+			const int sb = subof(raw[i].x);
+			code[t] = (unsigned)sb | (atomicAdd(&hist[sb], 1u) << 16);
+		}
+	}
 	__syncwarp();
-	{ // exclusive prefix: lane owns FWD_NSUB / 32 consecutive counters
+	{ // exclusive prefix in place: lane owns FWD_NSUB / 32 consecutive counters; hist[NSUB] = m
 		constexpr int PER = FWD_NSUB / 32;
 		unsigned v[PER], sum = 0;
 #pragma unroll
@@ -135,52 +173,399 @@ __device__ __forceinline__ void warp_sort_segment(uint4 *seg, int m, uint2 *so, 
 		unsigned run = warp_excl_scan_u32(sum, lane);
 #pragma unroll
 		for (int t = 0; t < PER; t++) { hist[lane * PER + t] = run; run += v[t]; }
+		if (lane == 31) hist[FWD_NSUB] = run;
 	}
 	__syncwarp();
-	for (int i = lane; i < m; i += 32) {
-		const unsigned long long key = akey[i];
-		const unsigned p = atomicAdd(&hist[subof((unsigned)(key >> 32))], 1u);
-		bkey[p] = key;
-		bval[p] = aval[i];
+#pragma unroll
+	for (int t = 0; t < FWD_PER; t++) {
+		if (32 * t >= m) break;
+		const int i = lane + 32 * t;
+		if (i < m) {
+			const uint4 e = raw[i];
+			const unsigned p = hist[code[t] & 0xffffu] + (code[t] >> 16);
+			bkey[p] = ((unsigned long long)e.x << 32) | e.y;
+			bval[p] = e.z;
+		}
 	}
 	__syncwarp();
-	// hist[s] is now the END of sub-bucket s
-	for (int p = lane; p < m; p += 32) {
-		const unsigned long long key = bkey[p];
-		const int s = subof((unsigned)(key >> 32));
-		const int lo = s ? (int)hist[s - 1] : 0, hi = (int)hist[s];
-		int r = lo;
-		for (int j = lo; j < hi; j++) r += bkey[j] < key;
-		const unsigned v = bval[p];
-		so[r] = make_uint2((unsigned)key, v);
-		seg[r] = make_uint4((unsigned)(key >> 32), (unsigned)key, v, 0u);
+#pragma unroll
+	for (int t = 0; t < FWD_PER; t++) {
+		if (32 * t >= m) break;
+		const int p = lane + 32 * t;
+		if (p < m) {
+			const unsigned long long key = bkey[p];
+			const int sb = subof((unsigned)(key >> 32));
+			const int lo = (int)hist[sb], hi = (int)hist[sb + 1];
+			int r = lo;
+			for (int j = lo; j < hi; j++) r += bkey[j] < key;
+			const unsigned v = bval[p];
+			if (SLOT) so[r] = make_uint2((unsigned)key, v);
+			seg[r] = make_uint4((unsigned)(key >> 32), (unsigned)key, v, 0u);
+		}
 	}
 }
 
-template <int RB>
-__global__ void __launch_bounds__(FwdCfg<RB>::NT, RB <= 8 ? 4 : 2)
-render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ loc,
-		  const uint32_t *__restrict__ binbase, const uint32_t *__restrict__ order, uint4 *entries,
-		  const float *__restrict__ bg, const float *__restrict__ beams,
-		  float *__restrict__ final_T, uint32_t *__restrict__ n_contrib, uint32_t *__restrict__ sorted_end,
-		  float4 *__restrict__ fin, uint4 *__restrict__ cta_prof, float *__restrict__ out_color,
-		  float *__restrict__ out_depth, float *__restrict__ out_occ, int sort_all, const FrameTotals *__restrict__ totals)
+// Segment iterator over a bin's depth buckets (bucket offsets in `sloc`, LGS_NB + 1 entries): the next segment at or
+// behind bucket k is buckets [k, k2), n entries starting at list position s0 (n = 0: none left).
+__device__ __forceinline__ void next_segment(const unsigned *sloc, int k, int &k2, unsigned &s0, unsigned &n)
+{
+	n = 0; k2 = k; s0 = 0;
+	while (k < LGS_NB) {
+		k2 = k; s0 = sloc[k]; n = 0;
+		while (k2 < LGS_NB) {
+			const unsigned c = sloc[k2 + 1] - sloc[k2];
+			if (n > 0 && n + c > FWD_CAP) break;
+			n += c;
+			k2++;
+			if (n >= FWD_TARGET) break;
+		}
+		if (n) return;
+		k = k2;
+	}
+}
+
+// The sorter warp of kernels A and C.  Walks the segments from bucket `k0` on; the raw entries of a (not oversized)
+// segment travel to shared memory as ONE bulk copy issued one segment ahead (it overlaps the sort of the previous
+// one); an oversized bucket is sorted in place in global memory.  `keep_going()` is asked before every segment
+// (laziness); `publish(seg position, chunk offset, count, sorted-from-shared?)` hands a sorted chunk on.  Returns the
+// list position up to which the bin is sorted.
+template <bool SLOT, class KeepGoing, class Acquire, class Publish>
+__device__ __forceinline__ unsigned run_sorter(unsigned char *ss, uint4 *ebin, unsigned ntotal, int k0, int lane,
+						KeepGoing keep_going, Acquire acquire_slot, Publish publish)
+{
+	const unsigned *sloc = reinterpret_cast<const unsigned *>(ss + SortSmem::LOC);
+	uint4 *raw = reinterpret_cast<uint4 *>(ss + SortSmem::RAW);
+	unsigned long long *bkey = reinterpret_cast<unsigned long long *>(ss + SortSmem::BKEY);
+	unsigned *bval = reinterpret_cast<unsigned *>(ss + SortSmem::BVAL);
+	unsigned *hist = reinterpret_cast<unsigned *>(ss + SortSmem::HIST);
+	const unsigned bar_raw = lgs_smem_addr(ss + SortSmem::BAR);
+	auto prefetch = [&](unsigned s0, unsigned n, unsigned buf) {
+		if (lane == 0) {
+			lgs_mbar_arrive_expect_tx(bar_raw + 8 * buf, n * 16u);
+			lgs_bulk_g2s(lgs_smem_addr(raw + buf * FWD_CAP), ebin + s0, n * 16u, bar_raw + 8 * buf);
+		}
+	};
+	unsigned rawpar = 0, buf = 0; // rawpar bit b: phase parity of landing buffer b's mbarrier
+	int k2, k2n;
+	unsigned s0, n, s0n, nn;
+	next_segment(sloc, k0, k2, s0, n);
+	bool inflight = false; // a bulk copy of the CURRENT segment is in flight into raw[buf]
+	if (n && n <= FWD_CAP) { prefetch(s0, n, buf); inflight = true; }
+	unsigned sorted_to = n ? s0 : ntotal;
+	while (n) {
+		if (!keep_going(sorted_to)) break; // nothing behind this point is read, sorted or gathered
+		next_segment(sloc, k2, k2n, s0n, nn);
+		uint4 *seg = ebin + s0;
+		const bool oversized = n > FWD_CAP;
+		if (oversized) warp_bitonic_sort_global(seg, (int)n, lane);
+		else {
+			lgs_mbar_wait(bar_raw + 8 * buf, (rawpar >> buf) & 1u); // the segment has landed in raw[buf]
+			rawpar ^= 1u << buf;
+			inflight = false;
+		}
+		bool inflight_next = false;
+		if (nn && nn <= FWD_CAP) { prefetch(s0n, nn, buf ^ 1u); inflight_next = true; } // overlaps the sort below
+		for (unsigned c0 = 0; c0 < n; c0 += FWD_CAP) {
+			const int m = (int)min((unsigned)FWD_CAP, n - c0);
+			uint2 *so = acquire_slot();
+			if (oversized) {
+				if (SLOT) {
+					for (int i = lane; i < m; i += 32) {
+						const uint4 e = seg[c0 + i];
+						so[i] = make_uint2(e.y, e.z);
+					}
+				}
+			} else {
+				warp_sort_segment<SLOT>(seg, raw + buf * FWD_CAP, m, so, bkey, bval, hist, lane);
+			}
+			publish(s0 + c0, m);
+		}
+		sorted_to = nn ? s0n : ntotal;
+		k2 = k2n; s0 = s0n; n = nn;
+		buf ^= 1u;
+		inflight = inflight_next;
+	}
+	if (inflight) lgs_mbar_wait(bar_raw + 8 * buf, (rawpar >> buf) & 1u); // never leave with a bulk copy in flight
+	return sorted_to;
+}
+
+// ---- kernel A: sort the prefix of every bin ----------------------------------------------------------------------
+__global__ void __launch_bounds__(FWD_GW * 32)
+sort_prefix_kernel(int nbins, const uint32_t *__restrict__ loc, const uint32_t *__restrict__ binbase, uint4 *entries,
+		   uint32_t *__restrict__ sorted_end, uint32_t *__restrict__ alive, const FrameTotals *__restrict__ totals)
 {
 	if (totals->overflow) return; // binning buffer too small for this frame: the host re-runs it (lgs_abi.cu)
-	using C = FwdCfg<RB>;
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int bin = blockIdx.x * FWD_GW + warp;
+	if (bin >= nbins) return; // warps are independent
+	unsigned char *ss = smem + (size_t)warp * SortSmem::BYTES;
+	unsigned *sloc = reinterpret_cast<unsigned *>(ss + SortSmem::LOC);
+	const unsigned base = binbase[bin], ntotal = binbase[bin + 1] - base;
+	for (int i = lane; i < LGS_NB; i += 32) sloc[i] = loc[(size_t)bin * LGS_NB + i];
+	if (lane == 0) {
+		sloc[LGS_NB] = ntotal;
+		lgs_mbar_init(lgs_smem_addr(ss + SortSmem::BAR), 1); // one arrive.expect_tx + the bulk copy's bytes
+		lgs_mbar_init(lgs_smem_addr(ss + SortSmem::BAR) + 8, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncwarp();
+	const unsigned se = run_sorter<false>(
+		ss, entries + base, ntotal, 0, lane, [&](unsigned sorted_to) { return sorted_to < FWD_PREFIX; },
+		[&]() { return (uint2 *)nullptr; }, [&](unsigned, int) {});
+	if (lane == 0) {
+		sorted_end[bin] = se;
+		alive[bin] = 0u;
+	}
+}
+
+// ---- a worker warp: one 32-pixel group (2 rows x 16 columns) of one bin --------------------------------------------
+struct GroupWorker {
+	// shared memory of this warp
+	float *tile; float4 *pf; float4 *sray; unsigned *pmask; uint2 *queue;
+	// identity
+	int lane, hrow, pcol, grp, row0, px, py;
+	unsigned lt;
+	bool inside;
+	const float4 *rec;
+	uint4 *ebin; // the bin's list
+	// pixel state (lanes = pixels: row 2 * grp + lane / 16, column lane % 16)
+	float T, C0, C1, D;
+	unsigned last, stop; // stop: list position + 1 of the entry that terminated the pixel (0: still alive)
+	bool done;
+	unsigned live, nchunks; // live: bit (row * 16 + column)
+	// pair queue (uniform) and the pending chunk: pairs whose records are in flight / in registers
+	int qhead, qn, pn;
+	uint2 ppair;
+	float4 pq0, pq1, pq2, pq3;
+
+	__device__ __forceinline__ void init(unsigned char *wb, const FrameGeom &g, int RB, int bin, int grp_, int lane_,
+					     const float *__restrict__ beams, const float4 *rec_, uint4 *ebin_, bool resume,
+					     const float *final_T, const uint32_t *n_contrib, const float4 *fin)
+	{
+		tile = reinterpret_cast<float *>(wb + WorkSmem::TILE);
+		pf = reinterpret_cast<float4 *>(wb + WorkSmem::PF);
+		sray = reinterpret_cast<float4 *>(wb + WorkSmem::RAY);
+		pmask = reinterpret_cast<unsigned *>(wb + WorkSmem::PMASK);
+		queue = reinterpret_cast<uint2 *>(wb + WorkSmem::QUEUE);
+		lane = lane_; grp = grp_; rec = rec_; ebin = ebin_;
+		hrow = lane >> 4; pcol = lane & 15;
+		const int tx = bin % g.gx, rg = bin / g.gx;
+		px = tx * LGS_TILE_X_ + pcol; py = rg * RB + 2 * grp + hrow;
+		inside = px < g.W && py < g.H && 2 * grp + hrow < RB;
+		row0 = rg * RB + 2 * grp;
+		lt = (1u << lane) - 1u;
+		T = 1.0f; C0 = 0.f; C1 = 0.f; D = 0.f; last = 0; stop = 0;
+		PixelRay ray = {0.f, 0.f, 0.f};
+		if (inside) {
+			ray = lgs_pixel_ray(px, py, g.W, g.H, beams);
+			if (resume) {
+				const size_t pix = (size_t)py * g.W + px;
+				const float4 f = fin[pix];
+				T = final_T[pix]; last = n_contrib[pix];
+				C0 = f.x; C1 = f.y; D = f.z; stop = __float_as_uint(f.w);
+			}
+		}
+		sray[pcol * 2 + hrow] = make_float4(ray.x, ray.y, ray.z, 0.f);
+		done = !inside || stop != 0u;
+		live = __ballot_sync(0xffffffffu, !done);
+		nchunks = 0;
+		qhead = 0; qn = 0; pn = 0;
+		ppair = make_uint2(0u, 0u);
+		pq0 = pq1 = pq2 = pq3 = make_float4(0.f, 0.f, 0.f, 0.f);
+		__syncwarp();
+	}
+
+	// evaluate + blend the pending chunk
+	__device__ __forceinline__ void process()
+	{
+		const bool valid = lane < pn;
+		const unsigned pos = ppair.y >> 1;
+		const int h = (int)(ppair.y & 1u);
+		float4 uu;
+		uu.x = lgs_dot_self(pq2.x, pq2.y, pq2.z);
+		uu.y = lgs_dot_self(pq3.x, pq3.y, pq3.z);
+		uu.z = lgs_div_prep(uu.x);
+		uu.w = lgs_div_prep(uu.y);
+		if (valid) pf[lane] = make_float4(pq2.w, pq3.w, pq1.w, __uint_as_float(pos));
+		const unsigned rs0 = __ballot_sync(0xffffffffu, valid && h == 0), rs1 = __ballot_sync(0xffffffffu, valid && h == 1);
+		const unsigned live0 = live & 0xffffu, live1 = live >> 16;
+		const unsigned mylive = valid ? (h ? live1 : live0) : 0u;
+		unsigned uni = (rs0 ? live0 : 0u) | (rs1 ? live1 : 0u); // columns with a live pixel in a row that has pairs
+		const unsigned rays = lgs_smem_addr(sray) + 16u * (unsigned)h;
+		const unsigned tcs = lgs_smem_addr(tile + lane);
+		const unsigned sel = (lane & 1) ? rs1 : rs0;
+		while (uni) { // two columns per trip: two independent dependency chains per lane
+			const int p0 = __ffs(uni) - 1;
+			uni &= uni - 1;
+			const int p1 = uni ? __ffs(uni) - 1 : p0; // odd count: the last column is evaluated twice (same value, same slot)
+			uni &= uni - 1;
+			const float4 r0 = lgs_lds128(rays + 32u * p0), r1 = lgs_lds128(rays + 32u * p1);
+			float a0 = 0.f, a1 = 0.f;
+			if (mylive) {
+				a0 = lgs_pair_alpha(r0.x, r0.y, r0.z, pq0, pq1, pq2, pq3, uu);
+				a1 = lgs_pair_alpha(r1.x, r1.y, r1.z, pq0, pq1, pq2, pq3, uu);
+			}
+			if (!((mylive >> p0) & 1u)) a0 = 0.f;
+			if (!((mylive >> p1) & 1u)) a1 = 0.f;
+			if (a0 != 0.f) lgs_sts32(tcs + (unsigned)(4 * FWD_TLD) * p0, a0);
+			if (a1 != 0.f) lgs_sts32(tcs + (unsigned)(4 * FWD_TLD) * p1, a1);
+			const unsigned b0 = __ballot_sync(0xffffffffu, a0 != 0.f), b1 = __ballot_sync(0xffffffffu, a1 != 0.f);
+			if (lane < 2) { // lane 0 publishes row 0's masks, lane 1 row 1's
+				pmask[lane * 16 + p0] = b0 & sel;
+				pmask[lane * 16 + p1] = b1 & sel;
+			}
+		}
+		__syncwarp();
+		// ---- blend: every lane walks the pairs that touch ITS pixel, in list order ----
+		unsigned blended = 0;
+		if (!done) {
+			unsigned mk = ((hrow ? rs1 : rs0) != 0u) ? pmask[lane] : 0u; // (a row without pairs was not visited: stale mask)
+			const float *trow = tile + (size_t)pcol * FWD_TLD;
+			while (mk) {
+				const int i = __ffs(mk) - 1;
+				mk &= mk - 1;
+				const float al = trow[i];
+				const float4 f = pf[i];
+				const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al));
+				if (test_T < 0.0001f) {
+					done = true;
+					stop = __float_as_uint(f.w) + 1u;
+					break;
+				}
+				C0 = __fmaf_rn(T, __fmul_rn(al, f.x), C0);
+				C1 = __fmaf_rn(T, __fmul_rn(al, f.y), C1);
+				D = __fmaf_rn(T, __fmul_rn(al, f.z), D);
+				T = test_T;
+				last = __float_as_uint(f.w) + 1u;
+				blended |= 1u << i;
+			}
+		}
+		// the backward pass skips (entry, row) pairs nothing was blended in: flags ride in the entry's spare word
+		const unsigned bl = __reduce_or_sync(0xffffffffu, blended);
+		if (valid && ((bl >> lane) & 1u)) atomicOr(&ebin[pos].w, 1u << (2 * grp + h));
+		live = __ballot_sync(0xffffffffu, !done);
+		nchunks++;
+		__syncwarp(); // tile / pf / pmask are free again
+	}
+	// take `nnew` pairs off the queue, start fetching their records, then work on the chunk fetched one step earlier
+	__device__ __forceinline__ void advance(int nnew)
+	{
+		uint2 npair = make_uint2(0u, 0u);
+		float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0, n2 = n0, n3 = n0;
+		if (lane < nnew) {
+			npair = queue[(qhead + lane) & (FWD_QCAP - 1)];
+			const float4 *r = rec + 4 * (size_t)npair.x;
+			n0 = r[0]; n1 = r[1]; n2 = r[2]; n3 = r[3];
+		}
+		qhead = (qhead + nnew) & (FWD_QCAP - 1);
+		qn -= nnew;
+		if (pn > 0) process();
+		pn = nnew; ppair = npair;
+		pq0 = n0; pq1 = n1; pq2 = n2; pq3 = n3;
+	}
+	// 32 sorted entries, one per lane (yp = y0 | y1 << 16 = getRect_lidar's y range, aux.h:80-92; 0 for a lane without an
+	// entry): which of this group's two rows does each rect cover?  Queue those pairs, work off full chunks.
+	__device__ __forceinline__ void scan32(unsigned id, unsigned yp, unsigned pos)
+	{
+		const int y0 = (int)(yp & 0xffffu), y1 = (int)(yp >> 16);
+		const bool c0 = row0 >= y0 && row0 < y1 && (live & 0xffffu) != 0u;
+		const bool c1 = row0 + 1 >= y0 && row0 + 1 < y1 && (live >> 16) != 0u;
+		const unsigned b0 = __ballot_sync(0xffffffffu, c0), b1 = __ballot_sync(0xffffffffu, c1);
+		if ((b0 | b1) == 0u) return;
+		const int off = qhead + qn + __popc(b0 & lt) + __popc(b1 & lt);
+		if (c0) queue[off & (FWD_QCAP - 1)] = make_uint2(id, pos << 1);
+		if (c1) queue[(off + (c0 ? 1 : 0)) & (FWD_QCAP - 1)] = make_uint2(id, (pos << 1) | 1u);
+		qn += __popc(b0) + __popc(b1);
+		__syncwarp();
+		while (qn >= 32 && live) advance(32);
+	}
+	// end of the list: work off what is queued and what is pending
+	__device__ __forceinline__ void flush()
+	{
+		while ((qn > 0 || pn > 0) && live) advance(min(qn, 32));
+	}
+	__device__ __forceinline__ void store(const FrameGeom &g, const float *__restrict__ bg, float *__restrict__ final_T,
+					      uint32_t *__restrict__ n_contrib, float4 *__restrict__ fin, float *__restrict__ out_color,
+					      float *__restrict__ out_depth, float *__restrict__ out_occ) const
+	{
+		if (!inside) return;
+		const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
+		final_T[pix] = T;
+		n_contrib[pix] = last;
+		fin[pix] = make_float4(C0, C1, D, __uint_as_float(stop));
+		out_color[pix] = __fmaf_rn(bg[0], T, C0);
+		out_color[HW + pix] = __fmaf_rn(bg[1], T, C1);
+		out_depth[pix] = D;
+		out_occ[pix] = __fsub_rn(1.0f, T);
+	}
+};
+
+// ---- kernel B: independent group warps over the sorted prefix ----------------------------------------------------
+template <int RB>
+__global__ void __launch_bounds__(FWD_GW * 32, 6)
+render_fwd_groups_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ binbase, uint4 *entries,
+			 const float *__restrict__ bg, const float *__restrict__ beams, float *__restrict__ final_T,
+			 uint32_t *__restrict__ n_contrib, const uint32_t *__restrict__ sorted_end, uint32_t *__restrict__ alive,
+			 float4 *__restrict__ fin, float *__restrict__ out_color, float *__restrict__ out_depth,
+			 float *__restrict__ out_occ, const FrameTotals *__restrict__ totals)
+{
+	if (totals->overflow) return;
+	constexpr int NPG = RB >= 2 ? RB / 2 : 1;
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int unit = blockIdx.x * FWD_GW + warp;
+	if (unit >= g.nbins * NPG) return; // warps are independent: no CTA barrier anywhere in this kernel
+	const int bin = unit / NPG, grp = unit % NPG;
+	const unsigned base = binbase[bin], ntotal = binbase[bin + 1] - base, sorted = sorted_end[bin];
+	uint4 *ebin = entries + base;
+	GroupWorker w;
+	w.init(smem + (size_t)warp * WorkSmem::BYTES, g, RB, bin, grp, lane, beams, rec, ebin, false, nullptr, nullptr, nullptr);
+	uint4 enext = make_uint4(0u, 0u, 0u, 0u);
+	if ((unsigned)lane < sorted) enext = ebin[lane];
+	for (unsigned j0 = 0; j0 < sorted && w.live; j0 += 32) {
+		const uint4 e = enext; // (lanes beyond the sorted prefix hold zeros: empty y range)
+		const unsigned jn = j0 + 32 + lane;
+		enext = make_uint4(0u, 0u, 0u, 0u);
+		if (jn < sorted) enext = ebin[jn];
+		w.scan32(e.y, e.z, j0 + (unsigned)lane);
+	}
+	w.flush(); // everything in the sorted prefix is blended; if the list goes on, kernel C resumes right behind it
+	w.store(g, bg, final_T, n_contrib, fin, out_color, out_depth, out_occ);
+	if (w.live && sorted < ntotal && lane == 0) alive[bin] = 1u; // rays still alive at the end of the prefix: kernel C goes on
+}
+
+// ---- kernel C: the tail of the bins whose rays outlive the sorted prefix --------------------------------------------
+template <int RB>
+__global__ void __launch_bounds__(TailCfg<RB>::NT, RB <= 8 ? 4 : 2)
+render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ loc,
+		       const uint32_t *__restrict__ binbase, uint4 *entries, const float *__restrict__ bg,
+		       const float *__restrict__ beams, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
+		       uint32_t *__restrict__ sorted_end, const uint32_t *__restrict__ alive, float4 *__restrict__ fin,
+		       uint4 *__restrict__ cta_prof, float *__restrict__ out_color, float *__restrict__ out_depth,
+		       float *__restrict__ out_occ, int sort_all, int full, const uint32_t *__restrict__ order,
+		       const FrameTotals *__restrict__ totals)
+{
+	if (totals->overflow) return; // binning buffer too small for this frame: the host re-runs it (lgs_abi.cu)
+	using C = TailCfg<RB>;
+	constexpr int NT = C::NT, NPG = C::NPG;
+	// full = 1: this kernel is the whole forward pass (no kernels A / B): every bin starts from scratch, in the launch
+	// order the scan prepared
+	const int bin = full ? (int)order[blockIdx.x] : (int)blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const unsigned base = binbase[bin], ntotal = binbase[bin + 1] - base, se0 = full ? 0u : sorted_end[bin];
+	if (!full && !(alive[bin] != 0u || (sort_all && se0 < ntotal))) { // kernel B finished this bin
+		if (tid == 0) cta_prof[bin] = make_uint4(0u, 0u, 0u, 0u);
+		return;
+	}
 	const long long clk0 = clock64();
 	const unsigned t0us = lgs_globaltimer_us();
-	constexpr int NT = C::NT, NPG = C::NPG;
 	extern __shared__ __align__(16) unsigned char smem[];
 	unsigned *sctl = reinterpret_cast<unsigned *>(smem + C::O_CTL); // [0] groups done, [1] warps finished, [2] chunks
 	uint4 *sdesc = reinterpret_cast<uint4 *>(smem + C::O_DESC);
-	unsigned *sloc = reinterpret_cast<unsigned *>(smem + C::O_LOC);
 	uint2 *slots = reinterpret_cast<uint2 *>(smem + C::O_SLOT);
+	unsigned char *ss = smem + C::O_SORT;
+	unsigned *sloc = reinterpret_cast<unsigned *>(ss + SortSmem::LOC);
 	const unsigned bar_full = lgs_smem_addr(smem + C::O_BAR), bar_empty = bar_full + 8 * FWD_NSLOT;
-
-	const int bin = (int)order[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int tx = bin % g.gx, rg = bin / g.gx;
-	const unsigned base = binbase[bin], ntotal = binbase[bin + 1] - base;
 	for (int i = tid; i < LGS_NB; i += NT) sloc[i] = loc[(size_t)bin * LGS_NB + i];
 	if (tid == 0) {
 		sloc[LGS_NB] = ntotal;
@@ -190,187 +575,50 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			lgs_mbar_init(bar_full + 8 * s, 32);         // all lanes of the sorter arrive
 			lgs_mbar_init(bar_empty + 8 * s, 32 * NPG);  // all lanes of every worker arrive
 		}
+		lgs_mbar_init(lgs_smem_addr(ss + SortSmem::BAR), 1); // landing buffers: one arrive.expect_tx + the bulk copy's bytes
+		lgs_mbar_init(lgs_smem_addr(ss + SortSmem::BAR) + 8, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads(); // the only CTA-wide barrier: from here on the warps only meet at the mbarriers
 
 	if (warp == NPG) {
 		// =============================== sorter warp ===============================
-		unsigned long long *akey = reinterpret_cast<unsigned long long *>(smem + C::O_AKEY);
-		unsigned long long *bkey = reinterpret_cast<unsigned long long *>(smem + C::O_BKEY);
-		unsigned *aval = reinterpret_cast<unsigned *>(smem + C::O_AVAL);
-		unsigned *bval = reinterpret_cast<unsigned *>(smem + C::O_BVAL);
-		unsigned *hist = reinterpret_cast<unsigned *>(smem + C::O_HIST);
 		const volatile unsigned *vdone = sctl;
+		int k0 = 0;
+		while (k0 < LGS_NB && sloc[k0] < se0) k0++; // kernel A sorted whole segments: the prefix ends at a bucket boundary
 		unsigned it = 0;
-		int k = 0;
-		while (k < LGS_NB) {
-			// ---- next segment: buckets [k, k2), n entries starting at list position s0 ----
-			int k2 = k;
-			const unsigned s0 = sloc[k];
-			unsigned n = 0;
-			while (k2 < LGS_NB) {
-				const unsigned c = sloc[k2 + 1] - sloc[k2];
-				if (n > 0 && n + c > FWD_CAP) break;
-				n += c;
-				k2++;
-				if (n >= FWD_TARGET) break;
-			}
-			if (n == 0) { k = k2; continue; }
-			if (!sort_all && vdone[0] >= (unsigned)NPG) break; // nothing behind this point is read, sorted or gathered
-			uint4 *seg = entries + base + s0;
-			const bool oversized = n > FWD_CAP;
-			if (oversized) warp_bitonic_sort_global(seg, (int)n, lane);
-			for (unsigned c0 = 0; c0 < n; c0 += FWD_CAP) {
-				const int m = (int)min((unsigned)FWD_CAP, n - c0);
+		const unsigned se = run_sorter<true>(
+			ss, entries + base, ntotal, k0, lane,
+			[&](unsigned) { return sort_all || vdone[0] < (unsigned)NPG; },
+			[&]() {
 				const unsigned slot = it % FWD_NSLOT, par = (it / FWD_NSLOT) & 1u;
 				lgs_mbar_wait(bar_empty + 8 * slot, par ^ 1u); // every worker has scanned the slot's previous contents
-				uint2 *so = slots + slot * FWD_CAP;
-				if (oversized) {
-					for (int i = lane; i < m; i += 32) {
-						const uint4 e = seg[c0 + i];
-						so[i] = make_uint2(e.y, e.z);
-					}
-				} else {
-					warp_sort_segment(seg, m, so, akey, bkey, aval, bval, hist, lane);
-				}
-				if (lane == 0) sdesc[slot] = make_uint4(s0 + c0, (unsigned)m, 0u, 0u);
+				return slots + slot * FWD_CAP;
+			},
+			[&](unsigned pos0, int m) {
+				const unsigned slot = it % FWD_NSLOT;
+				if (lane == 0) sdesc[slot] = make_uint4(pos0, (unsigned)m, 0u, 0u);
 				__syncwarp();
 				lgs_mbar_arrive(bar_full + 8 * slot);
 				it++;
-			}
-			k = k2;
-		}
+			});
 		{ // end marker
 			const unsigned slot = it % FWD_NSLOT, par = (it / FWD_NSLOT) & 1u;
 			lgs_mbar_wait(bar_empty + 8 * slot, par ^ 1u);
 			if (lane == 0) {
 				sdesc[slot] = make_uint4(0u, 0u, 1u, 0u);
-				sorted_end[bin] = (k < LGS_NB) ? sloc[k] : ntotal;
+				sorted_end[bin] = max(se, se0);
 			}
 			__syncwarp();
 			lgs_mbar_arrive(bar_full + 8 * slot);
 		}
 	} else {
-		// =============================== worker warp: pixel group `warp` ===============================
-		unsigned char *wb = smem + C::O_WORK + (size_t)warp * C::W_BYTES;
-		float *tile = reinterpret_cast<float *>(wb + C::W_TILE);
-		float4 *pf = reinterpret_cast<float4 *>(wb + C::W_PF);
-		float4 *sray = reinterpret_cast<float4 *>(wb + C::W_RAY);
-		unsigned *pmask = reinterpret_cast<unsigned *>(wb + C::W_PMASK);
-		uint2 *queue = reinterpret_cast<uint2 *>(wb + C::W_QUEUE);
-
-		// lanes = pixels in the blend: row 2 * warp + lane / 16, column lane % 16
-		const int hrow = lane >> 4, pcol = lane & 15;
-		const int px = tx * LGS_TILE_X_ + pcol, py = rg * RB + 2 * warp + hrow;
-		const bool inside = px < g.W && py < g.H && 2 * warp + hrow < RB;
-		float T = 1.0f, C0 = 0.f, C1 = 0.f, D = 0.f;
-		unsigned last = 0, stop = 0; // stop: list position of the entry that terminated the pixel (diagnostic)
-		bool done = !inside;
-		{
-			PixelRay ray = {0.f, 0.f, 0.f};
-			if (inside) ray = lgs_pixel_ray(px, py, g.W, g.H, beams);
-			sray[pcol * 2 + hrow] = make_float4(ray.x, ray.y, ray.z, 0.f);
-		}
-		unsigned live = __ballot_sync(0xffffffffu, !done); // bit (row * 16 + column)
-		bool gdone = live == 0;
+		// =============================== worker warp: pixel group `warp`, resumed from kernel B's state ===============
+		GroupWorker w;
+		w.init(smem + C::O_WORK + (size_t)warp * WorkSmem::BYTES, g, RB, bin, warp, lane, beams, rec, entries + base, !full, final_T,
+		       n_contrib, fin);
+		bool gdone = w.live == 0;
 		if (gdone && lane == 0) atomicAdd(&sctl[0], 1u);
-		__syncwarp();
-		const int row0 = rg * RB + 2 * warp; // image row of this group's first row
-		const unsigned lt = (1u << lane) - 1u;
-		unsigned nchunks = 0;
-
-		int qhead = 0, qn = 0;       // pair queue (uniform)
-		int pn = 0;                  // pending chunk: pairs whose records are in flight / in registers
-		uint2 ppair = make_uint2(0u, 0u);
-		float4 pq0 = make_float4(0.f, 0.f, 0.f, 0.f), pq1 = pq0, pq2 = pq0, pq3 = pq0;
-
-		// evaluate + blend the pending chunk
-		auto process = [&]() {
-			const bool valid = lane < pn;
-			const unsigned pos = ppair.y >> 1;
-			const int h = (int)(ppair.y & 1u);
-			float4 uu;
-			uu.x = lgs_dot_self(pq2.x, pq2.y, pq2.z);
-			uu.y = lgs_dot_self(pq3.x, pq3.y, pq3.z);
-			uu.z = lgs_div_prep(uu.x);
-			uu.w = lgs_div_prep(uu.y);
-			if (valid) pf[lane] = make_float4(pq2.w, pq3.w, pq1.w, __uint_as_float(pos));
-			const unsigned rs0 = __ballot_sync(0xffffffffu, valid && h == 0), rs1 = __ballot_sync(0xffffffffu, valid && h == 1);
-			const unsigned live0 = live & 0xffffu, live1 = live >> 16;
-			const unsigned mylive = valid ? (h ? live1 : live0) : 0u;
-			unsigned uni = (rs0 ? live0 : 0u) | (rs1 ? live1 : 0u); // columns with a live pixel in a row that has pairs
-			const unsigned rays = lgs_smem_addr(sray) + 16u * (unsigned)h;
-			const unsigned tcs = lgs_smem_addr(tile + lane);
-			const unsigned sel = (lane & 1) ? rs1 : rs0;
-			while (uni) { // two columns per trip: two independent dependency chains per lane
-				const int p0 = __ffs(uni) - 1;
-				uni &= uni - 1;
-				const int p1 = uni ? __ffs(uni) - 1 : p0; // odd count: the last column is evaluated twice (same value, same slot)
-				uni &= uni - 1;
-				const float4 r0 = lgs_lds128(rays + 32u * p0), r1 = lgs_lds128(rays + 32u * p1);
-				float a0 = 0.f, a1 = 0.f;
-				if (mylive) {
-					a0 = lgs_pair_alpha(r0.x, r0.y, r0.z, pq0, pq1, pq2, pq3, uu);
-					a1 = lgs_pair_alpha(r1.x, r1.y, r1.z, pq0, pq1, pq2, pq3, uu);
-				}
-				if (!((mylive >> p0) & 1u)) a0 = 0.f;
-				if (!((mylive >> p1) & 1u)) a1 = 0.f;
-				if (a0 != 0.f) lgs_sts32(tcs + (unsigned)(4 * FWD_TLD) * p0, a0);
-				if (a1 != 0.f) lgs_sts32(tcs + (unsigned)(4 * FWD_TLD) * p1, a1);
-				const unsigned b0 = __ballot_sync(0xffffffffu, a0 != 0.f), b1 = __ballot_sync(0xffffffffu, a1 != 0.f);
-				if (lane < 2) { // lane 0 publishes row 0's masks, lane 1 row 1's
-					pmask[lane * 16 + p0] = b0 & sel;
-					pmask[lane * 16 + p1] = b1 & sel;
-				}
-			}
-			__syncwarp();
-			// ---- blend: every lane walks the pairs that touch ITS pixel, in list order ----
-			unsigned blended = 0;
-			if (!done) {
-				unsigned mk = ((hrow ? rs1 : rs0) != 0u) ? pmask[lane] : 0u; // (a row without pairs was not visited: stale mask)
-				const float *trow = tile + (size_t)pcol * FWD_TLD;
-				while (mk) {
-					const int i = __ffs(mk) - 1;
-					mk &= mk - 1;
-					const float al = trow[i];
-					const float4 f = pf[i];
-					const float test_T = __fmul_rn(T, __fsub_rn(1.0f, al));
-					if (test_T < 0.0001f) {
-						done = true;
-						stop = __float_as_uint(f.w) + 1u;
-						break;
-					}
-					C0 = __fmaf_rn(T, __fmul_rn(al, f.x), C0);
-					C1 = __fmaf_rn(T, __fmul_rn(al, f.y), C1);
-					D = __fmaf_rn(T, __fmul_rn(al, f.z), D);
-					T = test_T;
-					last = __float_as_uint(f.w) + 1u;
-					blended |= 1u << i;
-				}
-			}
-			// the backward pass skips (entry, row) pairs nothing was blended in: flags ride in the entry's spare word
-			const unsigned bl = __reduce_or_sync(0xffffffffu, blended);
-			if (valid && ((bl >> lane) & 1u)) atomicOr(&entries[base + pos].w, 1u << (2 * warp + h));
-			live = __ballot_sync(0xffffffffu, !done);
-			nchunks++;
-			__syncwarp(); // tile / pf / pmask are free again
-		};
-		// take `nnew` pairs off the queue, start fetching their records, then work on the chunk fetched one step earlier
-		auto advance = [&](int nnew) {
-			uint2 npair = make_uint2(0u, 0u);
-			float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0, n2 = n0, n3 = n0;
-			if (lane < nnew) {
-				npair = queue[(qhead + lane) & (FWD_QCAP - 1)];
-				const float4 *r = rec + 4 * (size_t)npair.x;
-				n0 = r[0]; n1 = r[1]; n2 = r[2]; n3 = r[3];
-			}
-			qhead = (qhead + nnew) & (FWD_QCAP - 1);
-			qn -= nnew;
-			if (pn > 0) process();
-			pn = nnew; ppair = npair;
-			pq0 = n0; pq1 = n1; pq2 = n2; pq3 = n3;
-		};
-
 		unsigned it = 0;
 		for (;;) {
 			const unsigned slot = it % FWD_NSLOT, par = (it / FWD_NSLOT) & 1u;
@@ -380,25 +628,13 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			if (!gdone) {
 				const uint2 *so = slots + slot * FWD_CAP;
 				const int m = (int)d.y;
-				for (int j0 = 0; j0 < m; j0 += 32) {
-					// ---- scan 32 sorted entries: which of this group's two rows does each rect cover? ----
+				for (int j0 = 0; j0 < m && w.live; j0 += 32) {
 					const int j = j0 + lane;
 					uint2 e = make_uint2(0u, 0u);
 					if (j < m) e = so[j];
-					const int y0 = (int)(e.y & 0xffffu), y1 = (int)(e.y >> 16); // getRect_lidar's y range (aux.h:80-92); 0,0 for j >= m
-					const bool c0 = row0 >= y0 && row0 < y1 && (live & 0xffffu) != 0u;
-					const bool c1 = row0 + 1 >= y0 && row0 + 1 < y1 && (live >> 16) != 0u;
-					const unsigned b0 = __ballot_sync(0xffffffffu, c0), b1 = __ballot_sync(0xffffffffu, c1);
-					const int off = qhead + qn + __popc(b0 & lt) + __popc(b1 & lt);
-					const unsigned pos2 = (d.x + (unsigned)j) << 1;
-					if (c0) queue[off & (FWD_QCAP - 1)] = make_uint2(e.x, pos2);
-					if (c1) queue[(off + (c0 ? 1 : 0)) & (FWD_QCAP - 1)] = make_uint2(e.x, pos2 | 1u);
-					qn += __popc(b0) + __popc(b1);
-					__syncwarp();
-					while (qn >= 32 && live) advance(32);
-					if (live == 0) break;
+					w.scan32(e.x, e.y, d.x + (unsigned)j);
 				}
-				if (live == 0) {
+				if (w.live == 0) {
 					gdone = true;
 					if (lane == 0) atomicAdd(&sctl[0], 1u);
 				}
@@ -407,20 +643,9 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 			lgs_mbar_arrive(bar_empty + 8 * slot);
 			it++;
 		}
-		if (!gdone) { // end of the list: flush what is queued and what is pending
-			while ((qn > 0 || pn > 0) && live) advance(min(qn, 32));
-		}
-		if (lane == 0 && nchunks) atomicAdd(&sctl[2], nchunks);
-		if (inside) {
-			const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
-			final_T[pix] = T;
-			n_contrib[pix] = last;
-			fin[pix] = make_float4(C0, C1, D, __uint_as_float(stop));
-			out_color[pix] = __fmaf_rn(bg[0], T, C0);
-			out_color[HW + pix] = __fmaf_rn(bg[1], T, C1);
-			out_depth[pix] = D;
-			out_occ[pix] = __fsub_rn(1.0f, T);
-		}
+		if (!gdone) w.flush();
+		if (lane == 0 && w.nchunks) atomicAdd(&sctl[2], w.nchunks);
+		w.store(g, bg, final_T, n_contrib, fin, out_color, out_depth, out_occ);
 	}
 	__syncwarp();
 	if (lane == 0 && atomicAdd(&sctl[1], 1u) == (unsigned)C::NW - 1u) // last warp out: CTA diagnostics
@@ -429,26 +654,36 @@ render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *_
 
 template <int RB>
 void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries, const float *bg,
-		const float *beams, float *out_color, float *out_depth, float *out_occ, int sort_all, cudaStream_t st)
+		const float *beams, float *out_color, float *out_depth, float *out_occ, int sort_all, int split, cudaStream_t st)
 {
-	using C = FwdCfg<RB>;
-	cudaFuncSetAttribute(render_fwd_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
-	render_fwd_kernel<RB><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, gp.order, entries, bg, beams,
-								 ip.final_T, ip.n_contrib, ip.sorted_end, ip.fin, ip.cta_prof, out_color,
-								 out_depth, out_occ, sort_all, gp.totals);
+	using C = TailCfg<RB>;
+	constexpr int NPG = C::NPG;
+	cudaFuncSetAttribute(render_fwd_tail_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+	if (split) {
+		const size_t smA = FWD_GW * SortSmem::BYTES, smB = FWD_GW * WorkSmem::BYTES;
+		cudaFuncSetAttribute(sort_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
+		sort_prefix_kernel<<<(g.nbins + FWD_GW - 1) / FWD_GW, FWD_GW * 32, smA, st>>>(g.nbins, gp.loc, gp.binbase, entries,
+											     ip.sorted_end, ip.alive, gp.totals);
+		render_fwd_groups_kernel<RB><<<(g.nbins * NPG + FWD_GW - 1) / FWD_GW, FWD_GW * 32, smB, st>>>(
+			g, gp.rec, gp.binbase, entries, bg, beams, ip.final_T, ip.n_contrib, ip.sorted_end, ip.alive, ip.fin, out_color,
+			out_depth, out_occ, gp.totals);
+	}
+	render_fwd_tail_kernel<RB><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, bg, beams, ip.final_T,
+								     ip.n_contrib, ip.sorted_end, ip.alive, ip.fin, ip.cta_prof, out_color,
+								     out_depth, out_occ, sort_all, split ? 0 : 1, gp.order, gp.totals);
 }
 
 } // namespace
 
 void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries,
 			   const float *bg, const float *beams, float *out_color, float *out_depth, float *out_occ,
-			   int sort_all, cudaStream_t st)
+			   int sort_all, int split, cudaStream_t st)
 {
 	switch (g.RB) {
-	case 1: launch_fwd<1>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, st); break;
-	case 2: launch_fwd<2>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, st); break;
-	case 4: launch_fwd<4>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, st); break;
-	case 8: launch_fwd<8>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, st); break;
-	default: launch_fwd<16>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, st); break;
+	case 1: launch_fwd<1>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, st); break;
+	case 2: launch_fwd<2>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, st); break;
+	case 4: launch_fwd<4>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, st); break;
+	case 8: launch_fwd<8>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, st); break;
+	default: launch_fwd<16>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, st); break;
 	}
 }
