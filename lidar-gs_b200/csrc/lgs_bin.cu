@@ -8,8 +8,6 @@
 // order the reference's stable radix sort on tile|depth produces.
 #include "lgs_common.cuh"
 #include "lgs_kernels.h"
-#include <cstdio>
-#include <cstdlib>
 
 namespace {
 
@@ -158,27 +156,6 @@ scatter_kernel(int P, int gx, int RB, int far_, int near_, const uint4 *__restri
 	}
 }
 
-// TEMPORARY probe (LGS_PROBE=1): the same gathers, but a 4-byte store per instance instead of a 16-byte one
-__global__ void __launch_bounds__(256)
-scatter_probe_kernel(int P, int gx, int RB, int far_, int near_, const uint4 *__restrict__ aux, const uint32_t *__restrict__ ranks,
-		     const uint32_t *__restrict__ loc, const uint32_t *__restrict__ binbase, uint32_t *__restrict__ ids, unsigned capacity)
-{
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= P) return;
-	const uint4 a = aux[idx];
-	int x0 = a.x & 0xffff, nx = (int)(a.x >> 16) - x0, y0 = a.y & 0xffff, y1 = a.y >> 16;
-	int g0 = y0 / RB, ng = nx > 0 ? (y1 - 1) / RB - g0 + 1 : 0;
-	int n = nx > 0 ? nx * ng : 0;
-	const unsigned bucket = (unsigned)lgs_depth_bucket(__uint_as_float(a.z), far_, near_);
-#pragma unroll 4
-	for (int i = 0; i < n; i++) {
-		const int g = g0 + i / nx, x = x0 + i - (i / nx) * nx;
-		const size_t bb = (size_t)(g * gx + x) * LGS_NB + bucket;
-		const unsigned pos = binbase[g * gx + x] + loc[bb] + ranks[a.w + i];
-		if (pos < capacity) ids[pos] = (unsigned)idx;
-	}
-}
-
 } // namespace
 
 void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, unsigned capacity, cudaStream_t st)
@@ -193,21 +170,4 @@ void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, 
 {
 	scatter_kernel<<<(g.P + 255) / 256, 256, 0, st>>>(g.P, g.gx, g.RB, far_, near_, gp.aux, ranks, gp.loc, gp.binbase, entries,
 							  capacity, gp.totals);
-	static int probe = -1;
-	if (probe < 0) probe = getenv("LGS_PROBE") ? 1 : 0;
-	if (probe) { // TEMPORARY
-		static uint32_t *ids = nullptr;
-		static size_t idcap = 0;
-		if (idcap < capacity) { if (ids) cudaFree(ids); cudaMalloc(&ids, (size_t)capacity * 4); idcap = capacity; }
-		cudaEvent_t e0, e1;
-		cudaEventCreate(&e0); cudaEventCreate(&e1);
-		cudaEventRecord(e0, st);
-		scatter_probe_kernel<<<(g.P + 255) / 256, 256, 0, st>>>(g.P, g.gx, g.RB, far_, near_, gp.aux, ranks, gp.loc, gp.binbase, ids, capacity);
-		cudaEventRecord(e1, st);
-		cudaEventSynchronize(e1);
-		float ms = 0;
-		cudaEventElapsedTime(&ms, e0, e1);
-		fprintf(stderr, "[probe] 4-byte scatter: %.4f ms\n", ms);
-		cudaEventDestroy(e0); cudaEventDestroy(e1);
-	}
 }
