@@ -170,13 +170,22 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD},
+            "config": native_config(sc["P"], sc["H"], sc["W"], anc["means"].shape[0], 8, args.gpus, None),
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": "every step = one full cfg3 frame (filter+fwd+bwd) on the CPU restatement "
                                        "oracle/lgs_oracle.c (C + OpenMP); the reference ships no CPU rasterizer"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "extra": extra}
     print(json.dumps(line), flush=True)
+
+
+def native_config(P, H, W, A, rows_per_bin, world, exchange):
+    """`config` of the JSON line -- the same keys for the native and the reference arm (the driver compares them)."""
+    return {"workload": WORKLOAD, "P": int(P), "H": int(H), "W": int(W), "anchors": int(A), "rows_per_bin": int(rows_per_bin),
+            "parallelism": (f"frames sharded over {world} GPU(s), one exchange of the 13P fp32 parameter grads per step"
+                            + (f": {exchange}" if exchange else "")) if world > 1 else "1 GPU",
+            "l2": "no explicit flush: per-step working set (inputs 104 MB + records 128 MB + lists + 296 MB of "
+                  "gradient buffers) exceeds the 126 MB L2"}
 
 
 SURFEL_METRIC = "LiDAR range-view frames/sec (fwd+bwd), surfel path @5M surfels, 128x2048"
@@ -405,6 +414,97 @@ def run_surfel(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def other_workloads(dev, L, steps=30):
+    """extra.workloads: how the frame time moves with the workload -- BASELINE config 2, config 3 with opacities that never
+    saturate a ray, config 3 from a shifted pose (what rank 7 renders), config 5 (surfels) -- each next to the UNMODIFIED
+    reference CUDA source (oracle/_ref, compiled for sm_100a) on the same inputs, forward + backward, inputs resident."""
+    import torch
+    from lgs_b200 import capi, synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    out = {}
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        t = np.array([a.elapsed_time(b) for a, b in evs])
+        return {"ms_median": float(np.median(t)), "ms_p10": float(np.percentile(t, 10)), "ms_p90": float(np.percentile(t, 90)), "steps": n}
+
+    def ours_3d(sc):
+        d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
+        fr = capi.Frame(dev)
+        P, H, W = sc["P"], sc["H"], sc["W"]
+        o = dict(color=torch.empty((2, H, W), device=dev), depth=torch.empty((1, H, W), device=dev),
+                 occ=torch.empty((1, H, W), device=dev), radii=torch.empty((P,), dtype=torch.int32, device=dev))
+        f = lambda *s_: torch.empty(s_, dtype=torch.float32, device=dev)
+        g = dict(means2D=f(P, 4), opacities=f(P, 1), colors=f(P, 2), means3D=f(P, 3), cov3D=None, scales=f(P, 3), rotations=f(P, 4),
+                 scratch=torch.empty(L.lgs_backward_scratch_bytes(P), dtype=torch.uint8, device=dev))
+
+        def fn():
+            fr.forward(d["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"], d["viewmatrix"], d["beams"],
+                       H, W, sc["far"], sc["near"], out=o)
+            fr.backward(d["g_color"], d["g_depth"], d["g_occ"], grads=g)
+        r = timed(fn, steps)
+        r.update(num_rendered=int(fr.num_rendered), num_instances=int(fr.num_instances))
+        return r
+
+    def ref_3d(sc, n=5):
+        try:
+            import build_ref
+            import make_goldens as MG
+            ref = build_ref.load()
+            if ref is None:
+                return None
+            d = MG.to_dev(sc, dev)
+            return timed(lambda: MG.run_ref(ref, sc, dev, d=d), n)
+        except Exception as e:
+            return {"unavailable": repr(e)[:160]}
+
+    def entry(name, ours, ref):
+        e = {"this_repo": ours, "reference_cuda_sm100a": ref}
+        if ref and "ms_median" in ref:
+            e["speedup_vs_reference_cuda"] = ref["ms_median"] / ours["ms_median"]
+        out[name] = e
+        torch.cuda.empty_cache()
+
+    sc = synth.make_config(2)
+    entry("cfg2: 500k Gaussians, 64x1024, fwd+bwd", ours_3d(sc), ref_3d(sc))
+    sc = synth.make_config(CFG)
+    lo = dict(sc)
+    lo["opacities"] = np.random.default_rng(7).uniform(0.01, 0.1, sc["opacities"].shape).astype(np.float32)
+    entry("cfg3 with opacities U(0.01, 0.1) (rays do not saturate), fwd+bwd", ours_3d(lo), ref_3d(lo))
+    p7 = dict(sc)
+    p7["viewmatrix"] = rank_pose(sc, 7)
+    entry("cfg3 from the pose rank 7 renders, fwd+bwd", ours_3d(p7), ref_3d(p7))
+    del sc, lo, p7
+    try:
+        ss = synth.make_surfel_config(5)
+        d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in ss.items() if isinstance(v, np.ndarray)}
+        fr = capi.SurfelFrame(dev)
+
+        def sfn():
+            fr.forward(d["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"], d["viewmatrix"], d["beams"],
+                       ss["H"], ss["W"], ss["far"], ss["near"])
+            fr.backward(d["g_color"], d["g_others"])
+        ours = timed(sfn, 10)
+        ours.update(num_rendered=int(fr.num_rendered), num_instances=int(fr.num_instances))
+        del fr, d
+        torch.cuda.empty_cache()
+        ref = surfel_reference_cuda_timing(ss, iters=3)
+        if ref and "ms_per_step" in ref:
+            ref = {"ms_median": ref["ms_per_step"], "steps": ref["steps"]}
+        entry("cfg5: 5M surfels, 128x2048, fwd+bwd (surfel rasterizer)", ours, ref)
+    except Exception as e:
+        out["cfg5"] = {"unavailable": repr(e)[:200]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "surfel"],
@@ -414,8 +514,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--rows-per-bin", type=int, default=0)
-    ap.add_argument("--dense-allreduce", action="store_true",
-                    help="N > 1: all-reduce the dense 13P-float bucket instead of all-gathering the touched rows")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "sparse", "dense"],
+                    help="N > 1: peer = fused pack + pull over NVLink peer memory (default); sparse = NCCL all-gather of the "
+                         "packed rows; dense = NCCL all-reduce of the 13P-float bucket")
+    ap.add_argument("--dense-allreduce", action="store_true", help="same as --exchange dense")
+    ap.add_argument("--no-workloads", action="store_true", help="skip extra.workloads (other configs / poses, each vs the reference CUDA)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-dense-grads", action="store_true",
                     help="end-to-end leg copies the dense gradient arrays to the host instead of the non-zero rows")
@@ -466,9 +569,24 @@ def main():
     grads = dict(views, means2D=torch.empty((P, 4), device=dev), cov3D=None,
                  scratch=torch.empty(L.lgs_backward_scratch_bytes(P), dtype=torch.uint8, device=dev))
     fr = capi.Frame(dev)
-    xchg = None
-    if world > 1 and not args.dense_allreduce:
-        xchg = dp.SparseExchange(P, dev)
+    xchg, xmode = None, "dense"
+    if args.dense_allreduce:
+        args.exchange = "dense"
+    if world > 1 and args.exchange != "dense":
+        xmode = args.exchange
+        if xmode == "peer":
+            try:
+                xchg = dp.PeerExchange(P, dev)
+            except Exception as e:  # no peer access between the GPUs of this box: the NCCL path still works
+                print(f"[bench] rank {rank}: PeerExchange unavailable ({e!r}); using the NCCL all-gather", file=sys.stderr)
+                xmode = "sparse"
+            agree = torch.tensor([1 if xmode == "peer" else 0], device=dev)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)  # all ranks or none
+            if int(agree.item()) == 0 and xmode == "peer":
+                xchg.close()
+                xmode = "sparse"
+        if xmode == "sparse":
+            xchg = dp.SparseExchange(P, dev)
 
     def render():
         capi.visible_filter(a_means, a_scales3, a_rots, d["viewmatrix"], d["beams"], H, W, sc["far"], sc["near"])
@@ -476,12 +594,25 @@ def main():
                    d["beams"], H, W, sc["far"], sc["near"], out=out)
         fr.backward(d["g_color"], d["g_depth"], d["g_occ"], grads=grads)
 
-    def step():
-        render()
+    def exchange():
         if xchg is not None:
-            xchg.exchange(grads["scratch"], bucket, views)  # all-gather of the touched rows + local add == all-reduce
+            xchg.exchange(grads["scratch"], bucket, views)  # the other ranks' rows added locally == all-reduce
         elif world > 1:
             dist.all_reduce(bucket)
+
+    ev = []  # per timed step: (start, after the local frame, after the exchange)
+
+    def step(timed=False):
+        if timed:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+        render()
+        if timed:
+            e[1].record()
+        exchange()
+        if timed:
+            e[2].record()
+            ev.append(e)
 
     if xchg is not None:  # once, before anything is timed: the sparse exchange must equal the dense all-reduce
         render()
@@ -489,7 +620,7 @@ def main():
         dist.all_reduce(dense)
         xchg.exchange(grads["scratch"], bucket, views)
         err = float((bucket - dense).abs().max().item()) / max(float(dense.abs().max().item()), 1e-30)
-        assert err < 1e-5, f"sparse gradient exchange differs from the dense all-reduce: {err}"
+        assert err < 1e-5, f"{xmode} gradient exchange differs from the dense all-reduce: {err}"
         del dense
 
     def barrier():
@@ -501,7 +632,7 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    capi.timing_enable(True)
+    # ---- the timed region: K uninstrumented steps between two events ----
     n0 = L.lgs_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
@@ -512,9 +643,18 @@ def main():
     barrier()
     wall = time.time() - t0
     launches = L.lgs_launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    # ---- the same steps again with the library's per-stage events and per-step events (roofline, percentiles, per-rank split):
+    # kept out of the region above so that the instrumentation does not cost the headline anything ----
+    nstage = max(10, min(args.steps, 100))
+    capi.timing_enable(True)
+    for _ in range(nstage):
+        step(timed=True)
+    barrier()
     stages = capi.timing_collect()
     capi.timing_enable(False)
-    ms = e0.elapsed_time(e1)
+    if xmode == "peer" and xchg is not None:
+        xchg.status()  # raises if any step was skipped on the device (a rank had more rows than the buffer holds)
     if world > 1:
         tt = torch.tensor([ms], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -522,6 +662,22 @@ def main():
     ms_per_step = ms / args.steps
     value = world * 1e3 / ms_per_step
     R, V, Ninst = fr.num_rendered, int((out["radii"] > 0).sum().item()), fr.num_instances
+    # per rank: the local frame (filter + forward + backward) and the exchange (which includes waiting for slower ranks)
+    f_ms = np.array([e[0].elapsed_time(e[1]) for e in ev]); x_ms = np.array([e[1].elapsed_time(e[2]) for e in ev])
+    s_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
+    mine = [float(f_ms.mean()), float(x_ms.mean()), float(np.percentile(s_ms, 10)), float(np.median(s_ms)), float(np.percentile(s_ms, 90))]
+    if world > 1:
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+    else:
+        allr = [mine]
+    per_rank = [dict(rank=r, frame_ms=a[0], exchange_ms=a[1], step_ms_p10=a[2], step_ms_median=a[3], step_ms_p90=a[4])
+                for r, a in enumerate(allr)]
+    # Gaussians the backward pass of THIS rank visited (the library's own list), read before anything overwrites the scratch
+    import ctypes as _C
+    _ids, _cnt = _C.c_void_p(), _C.c_void_p()
+    L.lgs_backward_touched(_C.c_void_p(grads["scratch"].data_ptr()), P, _C.byref(_ids), _C.byref(_cnt))
+    touched_local = int(dp._device_u32(_cnt.value, dev).item())
 
     # ---- end to end through the reference-facing operator, host buffers ----
     e2e = None
@@ -696,7 +852,7 @@ def main():
     HW = H * W
     from lgs_b200.inspect import consumed_entries
     cons = consumed_entries(fr, H, W, args.rows_per_bin)
-    cons["touched"] = int((views["opacities"] != 0).sum().item()) if world == 1 else V
+    cons["touched"] = touched_local  # rank-local for every world size (the exchanged bucket holds the other ranks' rows too)
     alg = {  # bytes per launch
         "clear": 68.0 * P + 16.0 * cons["replayed"] + 80.0 * cons["touched"] + P / 8.0 + 8.0 * cons["nbins"] * 64,
         "project": 52.0 * P + 64.0 * V + 16.0 * P + 4.0 * P,
@@ -710,22 +866,32 @@ def main():
     per = {}
     for s, (tot_ms, n) in stages.items():
         if n:
-            per[s] = {"ms_per_step": tot_ms / args.steps, "launches_per_step": n / args.steps,
-                      "gbs": alg[s] / (tot_ms / args.steps * 1e-3) / 1e9}
+            per[s] = {"ms_per_step": tot_ms / nstage, "launches_per_step": n / nstage,
+                      "gbs": alg[s] / (tot_ms / nstage * 1e-3) / 1e9}
     dom = max((s for s in per if s != "clear"), key=lambda s: per[s]["ms_per_step"])
-    traffic = None
+    traffic, traffic_src = None, None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic, traffic_src = tj.get(dom), tj.get("_source")
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": per[dom]["gbs"], "peak": peak, "unit": "GB/s",
             "frac": per[dom]["gbs"] / peak, "traffic": traffic,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-            "alg_bytes_per_launch": alg[dom], "avg_launch_ms": per[dom]["ms_per_step"] / max(per[dom]["launches_per_step"], 1)}
+            "alg_bytes_per_launch": alg[dom], "avg_launch_ms": per[dom]["ms_per_step"] / max(per[dom]["launches_per_step"], 1),
+            "traffic_source": traffic_src,
+            "note": "the compositing kernels are bound by instruction issue, not by DRAM: their algorithmic bytes are the "
+                    "entries + records of the list prefixes actually consumed (extra.consumed), a few percent of the lists"}
     frame_bytes = 124.0 * P + 276.0 * V + 164.0 * R + 48.0 * HW  # SURVEY.md §8d full-sort byte model
     extra = {"num_rendered": R, "num_visible": V, "num_instances": Ninst, "consumed": cons,
              "stages": per, "frame_model_bytes": frame_bytes,
-             "frame_model_gbs": frame_bytes / (ms_per_step * 1e-3) / 1e9, "wall_s": wall}
+             "frame_model_note": "SURVEY 8d byte model of the reference's full-sort algorithm -- NOT traffic this implementation moves",
+             "per_rank": per_rank, "exchange": xmode if world > 1 else None,
+             "step_ms": {"p10": per_rank[0]["step_ms_p10"], "median": per_rank[0]["step_ms_median"], "p90": per_rank[0]["step_ms_p90"]},
+             "instrumented_steps": nstage,  # stages / step_ms / per_rank come from these (per-stage events cost ~0.05 ms a step)
+             "wall_s": wall}
+    if world == 1 and not args.no_workloads:
+        extra["workloads"] = other_workloads(dev, L)
 
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -743,15 +909,17 @@ def main():
                "sample": f"4 full cfg3 frames (filter+fwd+bwd), median of {['%.2f' % x for x in ts]} s, "
                          "oracle/lgs_oracle.c (C + OpenMP restatement; the reference ships no CPU rasterizer)"}
 
+    xdesc = None
+    if world > 1:
+        rows = xchg.last["rows"] if xchg is not None else 0
+        xdesc = {"peer": f"fused pack + pull of the touched rows over NVLink peer memory (<= {rows} rows x 64 B per rank), no host "
+                         "sync, verified equal to the dense all-reduce",
+                 "sparse": f"NCCL all-gather of the touched rows ({rows} x 64 B per rank) + local add, verified equal to the dense all-reduce",
+                 "dense": "dense NCCL all-reduce"}[xmode]
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "P": P, "H": H, "W": W, "anchors": A, "rows_per_bin": cons["rows_per_bin"],
-                       "parallelism": (f"frames sharded over {world} GPU(s), one exchange of the 13P fp32 parameter grads per step: " +
-                                       (f"all-gather of the touched rows ({xchg.last['rows']} x 64 B per rank, {xchg.last['mode']}) + local add, verified equal to the dense all-reduce"
-                                        if xchg is not None else "dense NCCL all-reduce")) if world > 1 else "1 GPU",
-                       "l2": "no explicit flush: per-step working set (inputs 104 MB + records 128 MB + lists + 296 MB of "
-                             "gradient buffers) exceeds the 126 MB L2"},
+            "config": native_config(P, H, W, A, cons["rows_per_bin"], world, xdesc),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "extra": extra}
     print(json.dumps(line), flush=True)

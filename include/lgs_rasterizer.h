@@ -190,6 +190,29 @@ int lgs_grad_scatter_add(int P, const float *gathered, int nranks, int my_rank, 
                          float *dL_dmean3D, float *dL_dscale, float *dL_drot,
                          float *dL_dopacity, float *dL_dcolor, void *stream);
 
+/*
+ * The same exchange as ONE pack + ONE pull kernel over peer memory (NVLink), no host synchronisation, no collective call:
+ * every rank owns a buffer of lgs_peer_buffer_bytes(cap) bytes (two slots of (cap + 1) 64-byte rows, zero-initialised)
+ * that the other ranks of the box have mapped (CUDA IPC); peer_buffers_dev is a DEVICE array of nranks pointers, entry r =
+ * the address of rank r's buffer in this process (entry my_rank = the local buffer).  `step` counts the exchanges (same
+ * value on every rank, starting at 0).  lgs_peer_pack fills slot (step & 1) of the local buffer and publishes it; lgs_peer_pull
+ * waits on the device for every rank's slot of the same step and adds the peers' rows into the local dense arrays.
+ * status_dev (2 device words, zero-initialised by the caller): [0] != 0 -> the step was NOT applied on any rank (1: a rank
+ * had more than cap rows; 2: a peer never published) and the caller must exchange densely instead; [1] = largest row count seen.
+ */
+size_t lgs_peer_buffer_bytes(int cap);
+void *lgs_peer_alloc(size_t bytes);                              /* zero-filled device buffer that peers can map; NULL on failure */
+int lgs_peer_free(void *buffer);
+int lgs_peer_export(void *buffer, unsigned char handle[64]);      /* CUDA IPC handle of a lgs_peer_alloc() buffer */
+void *lgs_peer_open(const unsigned char handle[64], int owner_device); /* map a peer's buffer (enables peer access); NULL on failure */
+int lgs_peer_close(void *mapped);
+int lgs_peer_pack(const uint32_t *ids, const uint32_t *count, int cap,
+		  const float *dL_dmean3D, const float *dL_dscale, const float *dL_drot, const float *dL_dopacity,
+		  const float *dL_dcolor, void *my_buffer, unsigned step, void *stream);
+int lgs_peer_pull(int P, int nranks, int my_rank, void *const *peer_buffers_dev, int cap, unsigned step,
+		  float *dL_dmean3D, float *dL_dscale, float *dL_drot, float *dL_dopacity, float *dL_dcolor,
+		  unsigned *status_dev, void *stream);
+
 /* ==== neural-Gaussian decode (the caller-side step in front of the rasterizer) =========
  * Fused replacement of gaussian_renderer/__init__.py:17-119 generate_neural_gaussians for the default model
  * configuration (use_feat_bank = False, appearance_dim = 0, color_channel = 2, feat_dim = 32): four MLPs

@@ -9,6 +9,7 @@
 // after which every rank holds the same sums a dense all-reduce would have produced.
 #include "../../include/lgs_rasterizer.h"
 #include "lgs_common.cuh"
+#include <cstring>
 
 namespace {
 
@@ -137,6 +138,149 @@ int lgs_grad_scatter_add(int P, const float *gathered, int nranks, int my_rank, 
 	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;
 }
 
+} // extern "C"
+
+// ---- fused exchange over peer memory (NVLink / NVSwitch) -------------------------------------------------------------------
+// The all-gather above needs the host twice per step (the row count sizes the collective) and moves every rank's rows
+// through NCCL's staging.  With the ranks' packed-row buffers mapped into each other's address space (CUDA IPC, set up
+// once by lgs_b200/dp.py) the exchange is two launches and no host involvement at all:
+//   lgs_peer_pack : rows -> slot (step & 1) of this rank's buffer (same 64-byte rows as lgs_grad_pack), then publishes
+//                   "slot complete" (a step number, system-scope release)
+//   lgs_peer_pull : for every peer waits on the DEVICE for the peer's flag (acquire), reads the peer's row count and
+//                   pulls exactly that many rows over NVLink, adding them into the local dense gradient arrays.  Only
+//                   the rows that exist cross the link.
+// Buffer per rank: 2 slots x { header 64 B: rows found | ready = step + 1 | - , rows [cap] x 64 B }.  Two slots are
+// enough without any further barrier: a rank can only write slot (k & 1) for step k after it has pulled step k - 1 from
+// every peer, i.e. after every peer has published step k - 1, which a peer does after it finished pulling step k - 2.
+// A peer with more rows than `cap` sets status[0] on every rank (all ranks see the same headers) and NOTHING is added on
+// any rank: the caller notices at its next status check and repeats the step's exchange densely.
+namespace {
+struct PeerHeader {
+	unsigned rows, ready, pad[14];
+};
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+	unsigned v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void peer_publish_kernel(PeerHeader *mine, unsigned step)
+{ // the pack kernel before it on the stream has completed: make its rows visible system-wide, then raise the flag
+	__threadfence_system();
+	st_release_sys(&mine->ready, step + 1u);
+}
+
+__global__ void __launch_bounds__(256)
+peer_pull_kernel(int P, int nranks, int my_rank, char *const *__restrict__ peers, size_t slot_off, int cap, unsigned step,
+		 float *__restrict__ d_means3D, float *__restrict__ d_scales, float *__restrict__ d_rot, float *__restrict__ d_opac,
+		 float *__restrict__ d_colors, unsigned *__restrict__ status)
+{
+	__shared__ unsigned s_rows[64];
+	__shared__ unsigned s_over;
+	if (threadIdx.x == 0) s_over = 0;
+	__syncthreads();
+	if (threadIdx.x < nranks) { // one thread per rank waits for that rank's slot (its own was published by lgs_peer_pack)
+		const PeerHeader *h = reinterpret_cast<const PeerHeader *>(peers[threadIdx.x] + slot_off);
+		const long long t0 = clock64();
+		while (ld_acquire_sys(&h->ready) < step + 1u) {
+			if (clock64() - t0 > 20000000000ll) { atomicExch(&status[0], 2u); break; } // ~10 s: a peer died; never hang the GPU
+			__nanosleep(200);
+		}
+		const unsigned n = ld_acquire_sys(&h->rows);
+		s_rows[threadIdx.x] = n;
+		if (n > (unsigned)cap) s_over = 1;
+	}
+	__syncthreads();
+	if (s_over) {
+		if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&status[0], 1u);
+		return;
+	}
+	for (int k = 1; k < nranks; k++) {
+		const int r = (my_rank + k) % nranks; // every rank starts with a different peer
+		const float4 *buf = reinterpret_cast<const float4 *>(peers[r] + slot_off);
+		const unsigned n = s_rows[r];
+		if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&status[1], n);
+		for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+			const float4 *row = buf + 4 * ((size_t)i + 1);
+			const float4 a = __ldcv(row), b = __ldcv(row + 1), c = __ldcv(row + 2), d = __ldcv(row + 3); // peer memory: never from a stale L1 line
+			const unsigned id = __float_as_uint(a.x);
+			if (id >= (unsigned)P) continue;
+			atomicAdd(d_means3D + 3 * (size_t)id, a.y); atomicAdd(d_means3D + 3 * (size_t)id + 1, a.z); atomicAdd(d_means3D + 3 * (size_t)id + 2, a.w);
+			atomicAdd(d_scales + 3 * (size_t)id, b.x); atomicAdd(d_scales + 3 * (size_t)id + 1, b.y); atomicAdd(d_scales + 3 * (size_t)id + 2, b.z);
+			atomicAdd(d_opac + id, b.w);
+			atomicAdd(d_rot + 4 * (size_t)id, c.x); atomicAdd(d_rot + 4 * (size_t)id + 1, c.y);
+			atomicAdd(d_rot + 4 * (size_t)id + 2, c.z); atomicAdd(d_rot + 4 * (size_t)id + 3, c.w);
+			atomicAdd(d_colors + 2 * (size_t)id, d.x); atomicAdd(d_colors + 2 * (size_t)id + 1, d.y);
+		}
+	}
+}
+} // namespace
+
+extern "C" {
+size_t lgs_peer_buffer_bytes(int cap) { return 2 * (((size_t)(cap > 0 ? cap : 0) + 1) * 64); }
+
+int lgs_peer_pack(const uint32_t *ids, const uint32_t *count, int cap, const float *dL_dmean3D, const float *dL_dscale,
+		  const float *dL_drot, const float *dL_dopacity, const float *dL_dcolor, void *my_buffer, unsigned step, void *stream)
+{
+	if (!ids || !count || cap < 0 || !dL_dmean3D || !dL_dscale || !dL_drot || !dL_dopacity || !dL_dcolor || !my_buffer) return LGS_EINVAL;
+	char *slot = (char *)my_buffer + (size_t)(step & 1u) * (((size_t)cap + 1) * 64);
+	if (cudaMemsetAsync(slot, 0, 4, (cudaStream_t)stream) != cudaSuccess) return LGS_ECUDA; // row counter only: `ready` keeps its (older) step
+	grad_pack_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(ids, count, cap, dL_dmean3D, dL_dscale, dL_drot, dL_dopacity, dL_dcolor,
+								     (float4 *)slot);
+	peer_publish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((PeerHeader *)slot, step);
+	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;
+}
+
+// Buffers the peers can map: plain cudaMalloc allocations (a caching-allocator sub-block cannot be exported as a whole)
+void *lgs_peer_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+	if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaFree(p); return nullptr; }
+	return p;
+}
+int lgs_peer_free(void *p) { return cudaFree(p) == cudaSuccess ? 0 : LGS_ECUDA; }
+int lgs_peer_export(void *buffer, unsigned char handle[64])
+{
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	cudaIpcMemHandle_t h;
+	if (!buffer || !handle || cudaIpcGetMemHandle(&h, buffer) != cudaSuccess) return LGS_ECUDA;
+	memcpy(handle, &h, 64);
+	return 0;
+}
+void *lgs_peer_open(const unsigned char handle[64], int owner_device)
+{
+	int cur = 0;
+	if (!handle || cudaGetDevice(&cur) != cudaSuccess) return nullptr;
+	if (owner_device != cur) {
+		const cudaError_t e = cudaDeviceEnablePeerAccess(owner_device, 0);
+		if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return nullptr; }
+		cudaGetLastError();
+	}
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, 64);
+	void *p = nullptr;
+	if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+int lgs_peer_close(void *p) { return cudaIpcCloseMemHandle(p) == cudaSuccess ? 0 : LGS_ECUDA; }
+
+int lgs_peer_pull(int P, int nranks, int my_rank, void *const *peer_buffers_dev, int cap, unsigned step, float *dL_dmean3D,
+		  float *dL_dscale, float *dL_drot, float *dL_dopacity, float *dL_dcolor, unsigned *status_dev, void *stream)
+{
+	if (P <= 0 || nranks < 1 || nranks > 64 || my_rank < 0 || my_rank >= nranks || cap < 0 || !peer_buffers_dev || !dL_dmean3D ||
+	    !dL_dscale || !dL_drot || !dL_dopacity || !dL_dcolor || !status_dev)
+		return LGS_EINVAL;
+	const size_t slot_off = (size_t)(step & 1u) * (((size_t)cap + 1) * 64);
+	peer_pull_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(P, nranks, my_rank, (char *const *)peer_buffers_dev, slot_off, cap, step,
+								 dL_dmean3D, dL_dscale, dL_drot, dL_dopacity, dL_dcolor, status_dev);
+	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;
+}
 } // extern "C"
 
 // ---- sparse read-back of a frame's gradients ---------------------------------------------------------------------------

@@ -17,7 +17,8 @@ SYMBOLS = ["lgs_forward", "lgs_backward", "lgs_backward_scratch_bytes", "lgs_vis
            "lgs_last_error", "lgs_version",
            "lgs_surfel_forward", "lgs_surfel_backward", "lgs_surfel_backward_scratch_bytes", "lgs_surfel_visible_filter",
            "lgs_surfel_mark_visible", "lgs_backward_touched", "lgs_grad_pack_bytes", "lgs_grad_count", "lgs_grad_pack", "lgs_grad_scatter_add",
-           "lgs_grad_rows_bytes", "lgs_grad_pack_nonzero"]
+           "lgs_grad_rows_bytes", "lgs_grad_pack_nonzero", "lgs_peer_buffer_bytes", "lgs_peer_pack", "lgs_peer_pull",
+           "lgs_peer_alloc", "lgs_peer_free", "lgs_peer_export", "lgs_peer_open", "lgs_peer_close"]
 
 
 def load():
@@ -66,6 +67,20 @@ def load():
     L.lgs_grad_pack_nonzero.argtypes = [i, vp, vp, vp, vp, vp, vp, i, vp, vp]
     L.lgs_grad_scatter_add.restype = i
     L.lgs_grad_scatter_add.argtypes = [i, vp, i, i, i, vp, vp, vp, vp, vp, vp]
+    L.lgs_peer_buffer_bytes.restype = C.c_size_t
+    L.lgs_peer_buffer_bytes.argtypes = [i]
+    L.lgs_peer_pack.restype = i
+    L.lgs_peer_pack.argtypes = [vp, vp, i, vp, vp, vp, vp, vp, vp, C.c_uint, vp]
+    L.lgs_peer_pull.restype = i
+    L.lgs_peer_pull.argtypes = [i, i, i, vp, i, C.c_uint, vp, vp, vp, vp, vp, vp, vp]
+    L.lgs_peer_alloc.restype = vp
+    L.lgs_peer_alloc.argtypes = [C.c_size_t]
+    L.lgs_peer_free.argtypes = [vp]
+    L.lgs_peer_export.restype = i
+    L.lgs_peer_export.argtypes = [vp, C.c_char_p]
+    L.lgs_peer_open.restype = vp
+    L.lgs_peer_open.argtypes = [C.c_char_p, i]
+    L.lgs_peer_close.argtypes = [vp]
     L.lgs_set_rows_per_bin.argtypes = [i]
     L.lgs_set_sort_all.argtypes = [i]
     L.lgs_set_forward_split.argtypes = [i]

@@ -186,6 +186,99 @@ class SparseExchange:
         self.last = dict(mode="sparse", rows=cap, bytes=int(nbytes))
 
 
+class PeerExchange:
+    """The step's exchange as ONE pack + ONE pull kernel over peer memory (csrc/lgs_dp.cu: lgs_peer_pack / lgs_peer_pull):
+    no collective call, no host synchronisation, and only the rows that exist cross NVLink.
+
+    Set-up (once): every rank allocates a packed-row buffer with the library (plain cudaMalloc, so that it can be
+    exported), the CUDA IPC handles travel through the process group's object all-gather, every rank maps every other
+    rank's buffer and uploads the table of pointers.  Per step: exchange() enqueues the two launches on the current
+    stream and returns; the ranks meet on DEVICE-side flags inside the pull kernel.  status() (a host read, call it
+    whenever convenient -- bench.py after the timed region) tells whether any step had to be skipped because a rank had
+    more rows than `cap`; cap only sizes the allocation (rows that do not exist are never moved), so it is generous."""
+
+    def __init__(self, P, device, group=None, cap=None):
+        import ctypes as C
+        from . import capi
+        self.capi, self.L = capi, capi.load()
+        self.P, self.dev, self.group = int(P), torch.device(device), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.cap = int(cap) if cap else max(65536, self.P // 8)
+        self.step = 0
+        self.last = dict(mode="none", rows=0, bytes=0)
+        self._mapped, self._buf = [], None
+        if self.world == 1:
+            return
+        L = self.L
+        with torch.cuda.device(self.dev):
+            nbytes = L.lgs_peer_buffer_bytes(self.cap)
+            self._buf = L.lgs_peer_alloc(nbytes)
+            if not self._buf:
+                raise capi.LgsError("lgs_peer_alloc failed")
+            h = C.create_string_buffer(64)
+            if L.lgs_peer_export(C.c_void_p(self._buf), h) < 0:
+                raise capi.LgsError("lgs_peer_export failed")
+            mine = (bytes(h.raw), int(self.dev.index if self.dev.index is not None else torch.cuda.current_device()))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=group)
+            ptrs = []
+            for r, (hb, owner) in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(int(self._buf))
+                    continue
+                p = L.lgs_peer_open(C.create_string_buffer(hb, 64), int(owner))
+                if not p:
+                    raise capi.LgsError(f"lgs_peer_open failed for rank {r} (device {owner}): no peer access?")
+                self._mapped.append(p)
+                ptrs.append(int(p))
+            self._ptrs = torch.tensor(ptrs, dtype=torch.int64, device=self.dev)
+            self._status = torch.zeros(2, dtype=torch.int32, device=self.dev)
+        dist.barrier(group=group)  # every buffer is mapped (and zero) before the first step touches one
+
+    def exchange(self, grad_scratch, bucket_flat, views, stream=None):
+        """Sum the step's gradients over the ranks, in place in `views`; nothing here waits for the device."""
+        if self.world == 1:
+            return
+        import ctypes as C
+        L = self.L
+        ids, cnt = C.c_void_p(), C.c_void_p()
+        if L.lgs_backward_touched(C.c_void_p(grad_scratch.data_ptr()), self.P, C.byref(ids), C.byref(cnt)) < 0:
+            raise self.capi.LgsError("lgs_backward_touched failed")
+        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream if stream is None else stream)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        g = (p(views["means3D"]), p(views["scales"]), p(views["rotations"]), p(views["opacities"]), p(views["colors"]))
+        with torch.cuda.device(self.dev):
+            if L.lgs_peer_pack(ids, cnt, self.cap, *g, C.c_void_p(self._buf), C.c_uint(self.step), st) < 0:
+                raise self.capi.LgsError("lgs_peer_pack failed")
+            if L.lgs_peer_pull(self.P, self.world, self.rank, p(self._ptrs), self.cap, C.c_uint(self.step), *g, p(self._status), st) < 0:
+                raise self.capi.LgsError("lgs_peer_pull failed")
+        self.step += 1
+        self.last = dict(mode="peer", rows=self.cap, bytes=0)
+
+    def status(self):
+        """Host read (synchronises): raises if a step was skipped; returns the largest row count any rank published."""
+        if self.world == 1:
+            return 0
+        flag, rows = (int(x) for x in self._status.cpu())
+        if flag == 1:
+            raise RuntimeError(f"PeerExchange: a rank packed more than cap = {self.cap} rows; the step was not applied "
+                               "(exchange it densely and enlarge cap)")
+        if flag == 2:
+            raise RuntimeError("PeerExchange: a peer never published its rows (timed out on the device)")
+        self.last = dict(mode="peer", rows=rows, bytes=rows * 64 * (self.world - 1))
+        return rows
+
+    def close(self):
+        if self.world > 1 and self._buf:
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=self.group)  # nobody is still pulling from a buffer that is about to go away
+            for m in self._mapped:
+                self.L.lgs_peer_close(m)
+            self.L.lgs_peer_free(self._buf)
+            self._mapped, self._buf = [], None
+
+
 def _device_u32(ptr, dev):
     """A 1-element int32 torch tensor aliasing the device word at `ptr` (the touched count inside the library's scratch)."""
     class _A:

@@ -215,6 +215,78 @@ def test_sparse_gradient_exchange_equals_dense_sum():
         assert torch.equal(got.flat, want) or float((got.flat - want).abs().max()) <= 1e-7 * float(want.abs().max())
 
 
+def test_peer_exchange_kernels_on_one_device():
+    """csrc/lgs_dp.cu: lgs_peer_pack / lgs_peer_pull with both "ranks" on ONE device (the buffers are then ordinary device
+    memory; across processes they are mapped by CUDA IPC, see tests/test_gpu_dp2.py): after two steps -- both slots of
+    the double buffer used -- every rank holds the dense sum of the two gradient buckets; a rank with more rows than the
+    buffer holds makes BOTH ranks skip the step and raises the status flag."""
+    import ctypes as C
+    import torch
+    from lgs_b200 import capi, dp, synth
+    L = capi.load()
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(P=30000, H=16, W=256, seed=79, pose="random")
+    sc.update(synth.make_upstream(16, 256, seed=79))
+    P = sc["P"]
+    d = util.to_torch(sc, dev)
+    xs = dp.SparseExchange(P, dev)
+    views_of = lambda b: {n: b.views[n] for n in ("means3D", "scales", "rotations", "opacities", "colors")}
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+
+    def render(r, shift):
+        view = d["viewmatrix"].clone()
+        view[3, 0] += shift * (r + 1)
+        fr = capi.Frame(dev)
+        fr.forward(d["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"], view, d["beams"], 16, 256, 80, 0)
+        b = dp.GradBucket(P, dev)
+        f = lambda *s_: torch.empty(s_, dtype=torch.float32, device=dev)
+        grads = dict(views_of(b), means2D=f(P, 4), cov3D=None,
+                     scratch=torch.empty(L.lgs_backward_scratch_bytes(P), dtype=torch.uint8, device=dev))
+        fr.backward(d["g_color"], d["g_depth"], d["g_occ"], grads=grads)
+        return b, grads
+
+    def run(cap, steps):
+        bufs = [L.lgs_peer_alloc(L.lgs_peer_buffer_bytes(cap)) for _ in range(2)]
+        assert all(bufs)
+        table = torch.tensor([int(b) for b in bufs], dtype=torch.int64, device=dev)
+        status = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in range(2)]
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        results = []
+        try:
+            for step in range(steps):
+                ranks = [render(r, 0.3 + 0.2 * step) for r in range(2)]
+                want = ranks[0][0].flat + ranks[1][0].flat
+                before = [b.flat.clone() for b, _ in ranks]
+                for r, (b, grads) in enumerate(ranks):  # every rank packs + publishes ...
+                    ids_ptr, cnt_ptr = xs.touched(grads["scratch"])
+                    v = views_of(b)
+                    assert L.lgs_peer_pack(C.c_void_p(ids_ptr), C.c_void_p(cnt_ptr), cap, ptr(v["means3D"]), ptr(v["scales"]), ptr(v["rotations"]),
+                                           ptr(v["opacities"]), ptr(v["colors"]), C.c_void_p(bufs[r]), C.c_uint(step), st) == 0
+                for r, (b, grads) in enumerate(ranks):  # ... then pulls the other's rows
+                    v = views_of(b)
+                    assert L.lgs_peer_pull(P, 2, r, ptr(table), cap, C.c_uint(step), ptr(v["means3D"]), ptr(v["scales"]), ptr(v["rotations"]),
+                                           ptr(v["opacities"]), ptr(v["colors"]), ptr(status[r]), st) == 0
+                torch.cuda.synchronize()
+                results.append((ranks, want, before))
+        finally:
+            torch.cuda.synchronize()
+            for b in bufs:
+                L.lgs_peer_free(C.c_void_p(b))
+        return results, [s_.cpu().tolist() for s_ in status]
+
+    results, status = run(cap=P, steps=3)
+    for ranks, want, _ in results:
+        for b, _g in ranks:
+            assert float((b.flat - want).abs().max()) <= 1e-6 * float(want.abs().max())
+    assert all(s_[0] == 0 and 0 < s_[1] < P for s_ in status), status
+    # far too small a buffer: nothing is applied on either rank, the flag says so
+    results, status = run(cap=8, steps=1)
+    ranks, want, before = results[0]
+    for (b, _g), b0 in zip(ranks, before):
+        assert torch.equal(b.flat, b0)
+    assert all(s_[0] == 1 for s_ in status), status
+
+
 def test_sparse_gradient_readback_is_lossless():
     """lgs_grad_pack_nonzero / dp.unpack_rows: the 80-byte rows of the Gaussians with a non-zero gradient rebuild every
     dense gradient array of the operator (the 13 parameter gradients and the 4-column means2D holder) exactly; a buffer

@@ -1,5 +1,5 @@
 for r in 0 1 2 4 7; do
-timeout 300 python bench.py --steps 100 --warmup 5 --no-e2e --no-cpu --pose-rank $r 2>&1 | tail -1 > gpurun_out/pose_$r.json
+timeout 300 python bench.py --steps 100 --warmup 5 --no-e2e --no-cpu --no-workloads --pose-rank $r 2>&1 | tail -1 > gpurun_out/pose_$r.json
 python - <<PY
 import json
 d=json.loads(open('gpurun_out/pose_$r.json').read())

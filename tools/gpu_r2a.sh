@@ -4,7 +4,7 @@ TAG=${1:-r02a}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_golden.py tests/test_gpu_oracle.py tests/test_gpu_fullsize.py tests/test_gpu_dropin.py -q --tb=short -p no:cacheprovider 2>&1 | tail -40 | tee gpurun_out/${TAG}_pytest.txt
 for r in 0 7; do
-timeout 300 python bench.py --steps 100 --warmup 5 --no-e2e --no-cpu --pose-rank $r 2>gpurun_out/${TAG}_bench_$r.err | tail -1 > gpurun_out/${TAG}_bench_$r.json
+timeout 300 python bench.py --steps 100 --warmup 5 --no-e2e --no-cpu --no-workloads --pose-rank $r 2>gpurun_out/${TAG}_bench_$r.err | tail -1 > gpurun_out/${TAG}_bench_$r.json
 tail -3 gpurun_out/${TAG}_bench_$r.err
 python - <<PY
 import json
