@@ -97,6 +97,95 @@ class FrameParallel:
         return self.bucket
 
 
+class TrainBucket:
+    """Train-mode data parallelism (second half): when the Gaussians are DECODED from anchors, what has to be
+    summed over the ranks' frames is the gradient of the model's own tensors -- `_anchor_feat [A,32]`, `_offset [A,K,3]`,
+    `_scaling [A,6]`, the weights of the four MLPs (scene/gaussian_model.py:372-390) -- and the per-step INCREMENTS of the
+    densification statistics (`opacity_accum`, `anchor_demon`, `offset_gradient_accum`, `offset_denom`, :599-620), so that
+    `adjust_anchor` sees the same numbers on every replica.
+
+    One flat fp32 buffer holds all of it.  `attach()` zeroes it and makes every parameter's `.grad` a view of it, so
+    autograd (and lgs_decode_backward underneath) accumulates straight into the message: no pack copy.  `stat_deltas` is an
+    object with the four accumulator names, views of the buffer's tail, to hand to `training_statis` instead of the model.
+    `all_reduce()` is the step's single collective; `apply_stats()` then adds the summed increments to the model's
+    persistent accumulators."""
+
+    def __init__(self, params, stats=None, group=None):
+        self.params = [p for p in params]
+        self.stats = dict(stats or {})
+        self.group = group
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params) + sum(t.numel() for t in self.stats.values())
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad_views, self._delta, o = [], {}, 0
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise ValueError("TrainBucket: float32 parameters only")
+            self.grad_views.append(self.flat[o:o + p.numel()].view(p.shape))
+            o += p.numel()
+        for name, t in self.stats.items():
+            self._delta[name] = self.flat[o:o + t.numel()].view(t.shape)
+            o += t.numel()
+        self.stat_deltas = type("StatDeltas", (), dict(self._delta))()
+
+    @property
+    def nbytes(self):
+        return self.flat.numel() * 4
+
+    def attach(self):
+        """Call before backward: the message is zeroed and every .grad points into it."""
+        self.flat.zero_()
+        for p, v in zip(self.params, self.grad_views):
+            p.grad = v
+        return self
+
+    def all_reduce(self, average=False, async_op=False):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return None
+        w = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+        if average and not async_op:
+            n_stats = sum(t.numel() for t in self.stats.values())
+            self.flat[:self.flat.numel() - n_stats].div_(dist.get_world_size(self.group))  # gradients only: statistics are counts
+        return w
+
+    def apply_stats(self):
+        for name, t in self.stats.items():
+            t.add_(self._delta[name])
+
+
+class synchronised_rng:
+    """`with dp.synchronised_rng(step):` -- every rank draws the SAME random numbers inside the block and gets its own
+    stream back afterwards.  The reference's `anchor_growing` thins its candidates with `torch.rand_like(...)`
+    (scene/gaussian_model.py:688); replicas that grow different anchors diverge for good, so the densification step of a
+    data-parallel run goes inside this block.  The base seed is agreed once (rank 0's, broadcast)."""
+    _base = None
+
+    def __init__(self, step, group=None, device=None):
+        self.step, self.group, self.device = int(step), group, device
+
+    @classmethod
+    def agree(cls, group=None, device=None, seed=None):
+        t = torch.tensor([int(seed) if seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,)).item())], dtype=torch.int64,
+                         device=device if device is not None else "cpu")
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.broadcast(t, src=0, group=group)
+        cls._base = int(t.item())
+        return cls._base
+
+    def __enter__(self):
+        if synchronised_rng._base is None:
+            synchronised_rng.agree(self.group, self.device)
+        self._cpu = torch.get_rng_state()
+        self._cuda = torch.cuda.get_rng_state_all() if torch.cuda.is_available() else None
+        torch.manual_seed((synchronised_rng._base * 1000003 + self.step) % (2 ** 63 - 1))  # seeds the CUDA generators too
+        return self
+
+    def __exit__(self, *a):
+        torch.set_rng_state(self._cpu)
+        if self._cuda is not None:
+            torch.cuda.set_rng_state_all(self._cuda)
+
+
 class SparseExchange:
     """The step's collective without the zeros (CUDA path only; csrc/lgs_dp.cu).
 

@@ -201,3 +201,72 @@ def test_world2_sparse_exchange_protocol(density, mode):
             assert last["rows"] % 1024 == 0 and last["rows"] >= max(g[4] for g in got)   # one capacity for everybody
             assert last["bytes"] == world * (last["rows"] + 1) * 64 < 13 * 4000 * 4
     assert got[0][3] == got[1][3]
+
+
+# ---- train-mode data parallelism: anchor / MLP gradients + statistics increments in one message, synchronised RNG ----
+def _train_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100)  # identical replicas ...
+        A, K = 50, 3
+        feat = torch.randn(A, 8, requires_grad=True)
+        offset = torch.randn(A, K, 3, requires_grad=True)
+        mlp = torch.nn.Sequential(torch.nn.Linear(8, 4), torch.nn.ReLU(), torch.nn.Linear(4, K))
+        params = [feat, offset] + list(mlp.parameters())
+        stats = dict(opacity_accum=torch.zeros(A, 1), anchor_demon=torch.zeros(A, 1), offset_gradient_accum=torch.zeros(A * K, 1),
+                     offset_denom=torch.zeros(A * K, 1))
+        stats["anchor_demon"] += 5.0  # history from earlier steps must survive
+        tb = dp.TrainBucket(params, stats)
+        torch.manual_seed(7 + rank)  # ... different frames
+        x = torch.randn(A, 8)
+        out = []
+        for step in range(2):
+            tb.attach()
+            loss = (mlp(feat * x).sum(dim=1) * offset.sum(dim=(1, 2))).sum() * (rank + 1)
+            loss.backward()
+            local = [p.grad.clone() for p in params]
+            assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, tb.grad_views))  # accumulated in place, no copy
+            tb.stat_deltas.opacity_accum += float(rank + 1)        # what training_statis would add for this rank's frame
+            tb.stat_deltas.offset_denom[rank::2] += 1.0
+            tb.all_reduce()
+            tb.apply_stats()
+            with dp.synchronised_rng(step):
+                same = torch.rand(4)
+            own = torch.rand(4)
+            out.append(dict(local=[g.numpy() for g in local], summed=[p.grad.detach().numpy().copy() for p in params], same=same.numpy(),
+                            own=own.numpy()))
+        q.put((rank, out, {k: v.numpy().copy() for k, v in stats.items()}, tb.nbytes))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_train_bucket_and_synchronised_rng():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict()
+    for _ in range(world):
+        r, out, stats, nbytes = q.get(timeout=120)
+        got[r] = (out, stats, nbytes)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (o0, s0, n0), (o1, s1, n1) = got[0], got[1]
+    assert n0 == n1 == 4 * (50 * 8 + 50 * 9 + 8 * 4 + 4 + 4 * 3 + 3 + 50 + 50 + 150 + 150)
+    for step in range(2):
+        for a, b, l0, l1 in zip(o0[step]["summed"], o1[step]["summed"], o0[step]["local"], o1[step]["local"]):
+            assert np.array_equal(a, b)                       # replicas hold the same gradient ...
+            assert np.allclose(a, l0 + l1, rtol=1e-6, atol=1e-7)  # ... the sum of the two frames'
+            assert np.abs(l0 - l1).max() > 0
+        assert np.array_equal(o0[step]["same"], o1[step]["same"])          # inside the block: the same draws
+        assert not np.array_equal(o0[step]["own"], o1[step]["own"])        # outside: every rank its own stream again
+    assert not np.array_equal(o0[0]["same"], o0[1]["same"])                # and a new draw every step
+    for k in s0:
+        assert np.array_equal(s0[k], s1[k])
+    assert np.all(s0["opacity_accum"] == 2 * (1.0 + 2.0)) and np.all(s0["anchor_demon"] == 5.0)
+    assert np.all(s0["offset_denom"] == 2.0)

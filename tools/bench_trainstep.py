@@ -20,9 +20,22 @@ import torch.nn.functional as F
 import diff_lidargs_rasterization as dlr
 from lgs_b200 import losses, neural_gaussians as ng, optim, statistics, synth
 
+from lgs_b200 import dp
+import torch.distributed as dist
+
 A, K, H, W = 333333, 6, 64, 2048
-dev = torch.device("cuda:0")
+# under torchrun (N > 1): train-mode data parallelism -- every rank its own frame (pose) of the same replicated model, ONE
+# all-reduce per iteration of the anchor / MLP gradients + the statistics increments (dp.TrainBucket)
+RANK, WORLD, LOCAL = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+dev = torch.device(f"cuda:{LOCAL}")
+torch.cuda.set_device(dev)
+if WORLD > 1:
+    dist.init_process_group("nccl", device_id=dev)
 sc = synth.make_scene(A, H, W, seed=1237)                     # anchors placed like the cfg3 Gaussians
+if RANK:
+    sys.path.insert(0, ROOT)
+    import bench
+    sc["viewmatrix"] = bench.rank_pose(sc, RANK)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 g = torch.Generator().manual_seed(11)
 anchor = t(sc["means3D"]).requires_grad_(True)
@@ -49,6 +62,9 @@ window = g1.mm(g1.t()).float().unsqueeze(0).unsqueeze(0).to(dev)
 stat = dict(opacity_accum=torch.zeros(A, 1, device=dev), anchor_demon=torch.zeros(A, 1, device=dev),
             offset_gradient_accum=torch.zeros(A * K, 1, device=dev), offset_denom=torch.zeros(A * K, 1, device=dev), n_offsets=K)
 PC = type("PC", (), stat)
+bucket = dp.TrainBucket(params, {k: v for k, v in stat.items() if k != "n_offsets"}) if WORLD > 1 else None
+if bucket is not None:
+    bucket.stat_deltas.n_offsets = K
 
 
 def eager_decode(vis):
@@ -87,8 +103,11 @@ opt_fused, opt_torch = optim.Adam(groups(), lr=0.0, eps=1e-15), torch.optim.Adam
 
 
 def iteration(fused, with_optimizer=False):
-    for p in params:
-        p.grad = None
+    if bucket is not None:
+        bucket.attach()  # .grad of every parameter = a zeroed view of the all-reduce message
+    else:
+        for p in params:
+            p.grad = None
     scaling_act = torch.exp(log_scaling)
     vis = rast.visible_filter(anchor.detach(), scaling_act.detach()[:, :3], torch.tensor([1.0, 0, 0, 0], device=dev).expand(A, 4).contiguous()) > 0
     if fused:
@@ -105,7 +124,10 @@ def iteration(fused, with_optimizer=False):
     loss = total + 0.01 * scaling.prod(dim=1).mean()
     loss.backward()
     if fused:
-        statistics.training_statis(PC, m2d, nop, radii > 0, mask, vis)
+        statistics.training_statis(PC if bucket is None else bucket.stat_deltas, m2d, nop, radii > 0, mask, vis)
+    if bucket is not None:
+        bucket.all_reduce()   # the iteration's single collective: gradients of anchors / offsets / scaling / MLPs + statistics
+        bucket.apply_stats()
     if with_optimizer:
         (opt_fused if fused else opt_torch).step()
     return loss.detach(), xyz.shape[0]
@@ -124,6 +146,22 @@ def timeit(fused, n=10, with_optimizer=False):
     return e0.elapsed_time(e1) / n
 
 
+if WORLD > 1:
+    ms = timeit(True, with_optimizer=True)
+    t_ = torch.tensor([ms], device=dev)
+    dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+    # replicas must agree bit for bit on what they are about to apply
+    chk = torch.stack([bucket.flat.double().sum(), bucket.flat.double().abs().sum()])
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if RANK == 0:
+        print(json.dumps(dict(op="data-parallel training iteration (filter + decode + rasterizer fwd/bwd + losses + statistics + "
+                                 "ONE all-reduce of anchor/MLP gradients and statistics increments + fused Adam)",
+                              n_gpus=WORLD, anchors=A, K=K, H=H, W=W, ms_per_iteration=float(t_.item()),
+                              frames_per_s=WORLD * 1e3 / float(t_.item()), message_bytes=bucket.nbytes,
+                              replicas_identical=bool(torch.equal(lo, hi)))))
+    dist.destroy_process_group()
+    sys.exit(0)
 lf, M = iteration(True)
 gf = feat.grad.clone()
 le, _ = iteration(False)
