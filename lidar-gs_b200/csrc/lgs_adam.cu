@@ -78,11 +78,11 @@ int lgs_adam_step(int ntensors, const lgs_adam_tensor *tensors, void *stream)
 		const lgs_adam_tensor &t = tensors[i];
 		if (t.numel < 0 || (t.numel && (!t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq))) return LGS_EINVAL;
 	}
-	for (int i0 = 0; i0 < ntensors; i0 += LGS_ADAM_MAX_TENSORS) {
+	for (int i = 0; i < ntensors;) { // batches of up to LGS_ADAM_MAX_TENSORS non-empty tensors; `i` carries over between batches
 		AdamArgs a;
 		a.nt = 0;
 		long long chunks = 0;
-		for (int i = i0; i < ntensors && a.nt < LGS_ADAM_MAX_TENSORS; i++) {
+		for (; i < ntensors && a.nt < LGS_ADAM_MAX_TENSORS; i++) {
 			if (tensors[i].numel == 0) continue;
 			chunks += (tensors[i].numel + ADAM_CHUNK - 1) / ADAM_CHUNK;
 			if (chunks > 0x7fffffffLL) return LGS_EINVAL;

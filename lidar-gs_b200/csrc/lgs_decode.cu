@@ -492,12 +492,9 @@ int lgs_decode_count(int Av, int K, const long long *vis_idx, const float *feat,
 	uint32_t *counts = (uint32_t *)scratch;
 	uint32_t *bsums = (uint32_t *)(scratch + lgs_al((size_t)Av * 4));
 	uint32_t *total = (uint32_t *)(scratch + lgs_al((size_t)Av * 4) + lgs_al((size_t)nb * 4));
-	static bool configured = false;
-	if (!configured) {
-		cudaFuncSetAttribute(decode_opacity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem_bytes(DEC_MAXK));
-		cudaFuncSetAttribute(decode_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem_bytes(DEC_MAXK));
-		configured = true;
-	}
+	// function attributes are per device: set on every call (a host-side table lookup), not once per process
+	cudaFuncSetAttribute(decode_opacity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem_bytes(DEC_MAXK));
+	cudaFuncSetAttribute(decode_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem_bytes(DEC_MAXK));
 	decode_opacity_kernel<<<nb, DEC_NT, decode_smem_bytes(K), st>>>(Av, K, vis_idx, feat, anchor, cam_center, *w, neural_opacity, mask,
 									  counts, bsums);
 	decode_scan_blocks_kernel<<<1, 1024, 0, st>>>(nb, bsums, total);
@@ -539,11 +536,8 @@ int lgs_decode_backward(int Av, int K, const long long *vis_idx, const float *fe
 	const int nb = (Av + DEC_NT - 1) / DEC_NT;
 	const uint32_t *counts = (const uint32_t *)scratch;
 	const uint32_t *bsums = (const uint32_t *)(scratch + lgs_al((size_t)Av * 4));
-	static bool configured = false;
-	if (!configured) {
-		cudaFuncSetAttribute(decode_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_bwd_smem_bytes(10));
-		configured = true;
-	}
+	// function attributes are per device: set on every call (a host-side table lookup), not once per process
+	cudaFuncSetAttribute(decode_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_bwd_smem_bytes(10));
 	const int grid = nb < 148 ? nb : 148;
 	decode_backward_kernel<<<grid, DBW_NT, decode_bwd_smem_bytes(K), (cudaStream_t)stream>>>(
 		Av, K, nb, vis_idx, feat, anchor, offset, scaling, cam_center, *w, neural_opacity, counts, bsums, g_xyz, g_color, g_opacity,

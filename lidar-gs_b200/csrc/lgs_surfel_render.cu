@@ -682,11 +682,8 @@ void launch_sfwd(const FrameGeom &g, const GeomPtrs &gp, const SurfelImagePtrs &
 		 const float *beams, float *out_color, float *out_others, int sort_all, cudaStream_t st)
 {
 	using C = SFwdCfg<RB>;
-	static bool configured = false;
-	if (!configured) {
-		cudaFuncSetAttribute(surfel_render_fwd_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
-		configured = true;
-	}
+	// function attributes are per device: set on every call (a host-side table lookup), not once per process
+	cudaFuncSetAttribute(surfel_render_fwd_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
 	surfel_render_fwd_kernel<RB><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, gp.order, entries, bg, beams,
 									ip.final_T, ip.n_contrib, ip.sorted_end, ip.finA, ip.finB, out_color,
 									out_others, sort_all, gp.totals);
@@ -711,11 +708,8 @@ void lgs_launch_surfel_render_bwd(const FrameGeom &g, const GeomPtrs &gp, const 
 				  cudaStream_t st)
 {
 	using C = SBwdCfg;
-	static bool configured = false;
-	if (!configured) {
-		cudaFuncSetAttribute(surfel_render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
-		configured = true;
-	}
+	// function attributes are per device: set on every call (a host-side table lookup), not once per process
+	cudaFuncSetAttribute(surfel_render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
 	const int npgl = g.RB >= 2 ? g.RB / 2 : 1;
 	surfel_render_bwd_kernel<<<g.nbins * npgl, C::NT, C::BYTES, st>>>(g, gp.rec, gp.binbase, gp.order, entries, bg, beams, ip.final_T,
 									   ip.n_contrib, ip.finA, ip.finB, dL_dpix, dL_dothers, grad);

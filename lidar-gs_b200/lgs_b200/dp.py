@@ -194,7 +194,11 @@ class SparseExchange:
     (64 B each), the ranks all-gather them, and each rank adds the others' rows into its own dense gradient arrays:
     the same sums, a few MB instead of 104 MB on the wire.  Per step: one 4-byte all-reduce(MAX) of the row count
     (sizes the gather; read on the host), one all-gather.  Falls back to the dense all-reduce when the packed rows
-    would not be smaller than the bucket."""
+    would not be smaller than the bucket.
+
+    ONE backward per exchange: the touched list is the one the last lgs_backward left in `grad_scratch`.  A rank that
+    accumulates several frames into the bucket before exchanging (FrameParallel.step with more frames than ranks) must use
+    the dense all-reduce -- rows touched only by an earlier frame are not in the list."""
 
     def __init__(self, P, device, group=None):
         from . import capi
@@ -284,7 +288,8 @@ class PeerExchange:
     rank's buffer and uploads the table of pointers.  Per step: exchange() enqueues the two launches on the current
     stream and returns; the ranks meet on DEVICE-side flags inside the pull kernel.  status() (a host read, call it
     whenever convenient -- bench.py after the timed region) tells whether any step had to be skipped because a rank had
-    more rows than `cap`; cap only sizes the allocation (rows that do not exist are never moved), so it is generous."""
+    more rows than `cap`; cap only sizes the allocation (rows that do not exist are never moved), so it is generous.
+    Like SparseExchange: one backward per exchange (the rows come from the touched list of the last lgs_backward)."""
 
     def __init__(self, P, device, group=None, cap=None):
         import ctypes as C

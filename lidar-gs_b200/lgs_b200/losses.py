@@ -56,8 +56,10 @@ class _LossFn(torch.autograd.Function):
         values = torch.empty(6, dtype=torch.float32, device=dev)
         p = lambda t: C.c_void_p(t.data_ptr())
         st = torch.cuda.current_stream(dev).cuda_stream
-        if _lib().lgs_loss_forward(H, W, p(img), p(dep), p(gt), p(win), float(lambda_dssim), p(maps), p(sums), p(values),
-                                   C.c_void_p(st)) < 0:
+        with torch.cuda.device(dev):
+            rc = _lib().lgs_loss_forward(H, W, p(img), p(dep), p(gt), p(win), float(lambda_dssim), p(maps), p(sums), p(values),
+                                         C.c_void_p(st))
+        if rc < 0:
             raise capi.LgsError("lgs_loss_forward failed")
         ctx.save_for_backward(img, dep, gt, maps)
         ctx.lam = float(lambda_dssim)
@@ -73,8 +75,10 @@ class _LossFn(torch.autograd.Function):
         d_image, d_depth = torch.empty_like(img), torch.empty_like(dep)
         p = lambda t: C.c_void_p(t.data_ptr())
         st = torch.cuda.current_stream(dev).cuda_stream
-        if _lib().lgs_loss_backward(H, W, p(img), p(dep), p(gt), p(_window(dev)), p(maps), ctx.lam, p(d_image), p(d_depth),
-                                    C.c_void_p(st)) < 0:
+        with torch.cuda.device(dev):
+            rc = _lib().lgs_loss_backward(H, W, p(img), p(dep), p(gt), p(_window(dev)), p(maps), ctx.lam, p(d_image), p(d_depth),
+                                          C.c_void_p(st))
+        if rc < 0:
             raise capi.LgsError("lgs_loss_backward failed")
         return d_image * g_total, d_depth * g_total, None, None
 

@@ -107,9 +107,10 @@ class _DecodeFn(torch.autograd.Function):
             gn = None if g_nop is None else g_nop.contiguous().float()
             p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
             st = torch.cuda.current_stream(dev).cuda_stream
-            rc = L.lgs_decode_backward(Av, K, p(ctx.vis_idx), p(feat), p(anchor), p(offset), p(scaling), p(cam), C.byref(W),
-                                       p(neural_opacity), p(scratch), p(gx), p(gc), p(go), p(gs), p(gr), p(gn), p(d_feat),
-                                       p(d_anchor), p(d_offset), p(d_scaling), p(dW), C.c_void_p(st))
+            with torch.cuda.device(dev):
+                rc = L.lgs_decode_backward(Av, K, p(ctx.vis_idx), p(feat), p(anchor), p(offset), p(scaling), p(cam), C.byref(W),
+                                           p(neural_opacity), p(scratch), p(gx), p(gc), p(go), p(gs), p(gr), p(gn), p(d_feat),
+                                           p(d_anchor), p(d_offset), p(d_scaling), p(dW), C.c_void_p(st))
             if rc < 0:
                 raise capi.LgsError("lgs_decode_backward failed")
             del keep
@@ -127,6 +128,11 @@ class _DecodeFn(torch.autograd.Function):
 
 
 def _forward(feat, anchor, offset, scaling, cam, vis_idx, wts):
+    with torch.cuda.device(feat.device):  # the library launches on the CURRENT device: make it the tensors' device
+        return _forward_impl(feat, anchor, offset, scaling, cam, vis_idx, wts)
+
+
+def _forward_impl(feat, anchor, offset, scaling, cam, vis_idx, wts):
     dev = feat.device
     L = _lib()
     A, K = anchor.shape[0], offset.shape[1]

@@ -48,7 +48,8 @@ def training_statis(pc, viewspace_point_tensor, opacity, update_filter, offset_s
             raise ValueError(f"pc.{name} must be a contiguous float32 CUDA tensor")
     p = lambda t: C.c_void_p(t.data_ptr())
     st = torch.cuda.current_stream(dev).cuda_stream
-    rc = _lib().lgs_training_statis(A, K, p(vis), p(vis_rank), p(op), p(sel), p(sel_rank), p(upd), p(g), p(pc.opacity_accum),
+    with torch.cuda.device(dev):
+        rc = _lib().lgs_training_statis(A, K, p(vis), p(vis_rank), p(op), p(sel), p(sel_rank), p(upd), p(g), p(pc.opacity_accum),
                                     p(pc.anchor_demon), p(pc.offset_gradient_accum), p(pc.offset_denom), C.c_void_p(st))
     if rc < 0:
         raise capi.LgsError("lgs_training_statis failed")

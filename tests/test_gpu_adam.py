@@ -142,3 +142,23 @@ def test_many_tensors_unaligned_views_and_errors():
     p = torch.nn.Parameter(torch.ones(4, device=DEV))
     optim.Adam([p], lr=0.1).step()                   # nothing has a gradient: a no-op
     assert float(p.detach().sum()) == 4.0
+
+
+def test_more_than_one_launch_worth_of_tensors_with_empty_ones():
+    """Host batching of lgs_adam_step: empty tensors are skipped inside a batch of 48, so a batch can consume more than 48
+    table entries; the next batch must start where the previous one stopped, not 48 entries further (which would apply the
+    update twice to the tensors in between)."""
+    from lgs_b200 import optim
+    g = torch.Generator().manual_seed(12)
+    sizes = ([0, 5, 0, 9] * 13 + [17] * 30 + [0, 3] * 10)  # 102 entries, 26 + ... empties inside the first batches
+    pa = [torch.nn.Parameter(torch.randn(n, generator=g).to(DEV)) for n in sizes]
+    pb = [torch.nn.Parameter(x.detach().clone()) for x in pa]
+    oa, ob = optim.Adam(pa, lr=0.01, eps=1e-15), torch.optim.Adam(pb, lr=0.01, eps=1e-15)
+    for _ in range(2):
+        for x, y in zip(pa, pb):
+            gr = torch.randn(x.shape, generator=g).to(DEV)
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+    for i, (x, y) in enumerate(zip(pa, pb)):
+        assert same_bits(x.detach(), y.detach()), i
