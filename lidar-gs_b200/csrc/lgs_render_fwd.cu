@@ -395,25 +395,33 @@ struct GroupWorker {
 		const unsigned rays = lgs_smem_addr(sray) + 16u * (unsigned)h;
 		const unsigned tcs = lgs_smem_addr(tile + lane);
 		const unsigned sel = (lane & 1) ? rs1 : rs0;
-		while (uni) { // two columns per trip: two independent dependency chains per lane
-			const int p0 = __ffs(uni) - 1;
-			uni &= uni - 1;
-			const int p1 = uni ? __ffs(uni) - 1 : p0; // odd count: the last column is evaluated twice (same value, same slot)
-			uni &= uni - 1;
-			const float4 r0 = lgs_lds128(rays + 32u * p0), r1 = lgs_lds128(rays + 32u * p1);
-			float a0 = 0.f, a1 = 0.f;
-			if (mylive) {
-				a0 = lgs_pair_alpha(r0.x, r0.y, r0.z, pq0, pq1, pq2, pq3, uu);
-				a1 = lgs_pair_alpha(r1.x, r1.y, r1.z, pq0, pq1, pq2, pq3, uu);
+		while (uni) { // four columns per trip: four independent dependency chains per lane (latency of the per-pair chain
+			      // -- ~35 dependent instructions, one MUFU -- is what bounds a lone warp on a long list)
+			int pc_[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) { // fewer than four left: the last column is evaluated again (same value, same slot)
+				pc_[u] = uni ? __ffs(uni) - 1 : pc_[u > 0 ? u - 1 : 0];
+				uni &= uni - 1;
 			}
-			if (!((mylive >> p0) & 1u)) a0 = 0.f;
-			if (!((mylive >> p1) & 1u)) a1 = 0.f;
-			if (a0 != 0.f) lgs_sts32(tcs + (unsigned)(4 * FWD_TLD) * p0, a0);
-			if (a1 != 0.f) lgs_sts32(tcs + (unsigned)(4 * FWD_TLD) * p1, a1);
-			const unsigned b0 = __ballot_sync(0xffffffffu, a0 != 0.f), b1 = __ballot_sync(0xffffffffu, a1 != 0.f);
+			float4 rr[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) rr[u] = lgs_lds128(rays + 32u * pc_[u]);
+			float al[4] = {0.f, 0.f, 0.f, 0.f};
+			if (mylive) {
+#pragma unroll
+				for (int u = 0; u < 4; u++) al[u] = lgs_pair_alpha(rr[u].x, rr[u].y, rr[u].z, pq0, pq1, pq2, pq3, uu);
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				if (!((mylive >> pc_[u]) & 1u)) al[u] = 0.f;
+				if (al[u] != 0.f) lgs_sts32(tcs + (unsigned)(4 * FWD_TLD) * pc_[u], al[u]);
+			}
+			unsigned bm[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) bm[u] = __ballot_sync(0xffffffffu, al[u] != 0.f);
 			if (lane < 2) { // lane 0 publishes row 0's masks, lane 1 row 1's
-				pmask[lane * 16 + p0] = b0 & sel;
-				pmask[lane * 16 + p1] = b1 & sel;
+#pragma unroll
+				for (int u = 0; u < 4; u++) pmask[lane * 16 + pc_[u]] = bm[u] & sel;
 			}
 		}
 		__syncwarp();
