@@ -139,8 +139,13 @@ scatter_kernel(int P, int gx, int RB, int far_, int near_, const uint4 *__restri
 	};
 	const uint4 e = make_uint4(a.z, (unsigned)idx, a.y, 0u);
 	if (n < LGS_COOP_MIN) {
+		int bx = 0, brow = g0 * gx + x0; // same row-by-row walk as lgs_emit_instances, no integer division per instance
 #pragma unroll 4
-		for (int i = 0; i < n; i++) emit(x0, nx, g0, bucket, a.w, e, i);
+		for (int i = 0; i < n; i++) {
+			const unsigned pos = binbase[brow + bx] + loc[(size_t)(brow + bx) * LGS_NB + bucket] + ranks[a.w + i];
+			if (pos < capacity) entries[pos] = e;
+			if (++bx == nx) { bx = 0; brow += gx; }
+		}
 	}
 	unsigned big = __ballot_sync(0xffffffffu, n >= LGS_COOP_MIN);
 	while (big) {

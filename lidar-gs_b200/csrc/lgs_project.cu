@@ -176,24 +176,27 @@ __device__ __forceinline__ void load_beam_tables(const float *__restrict__ beams
 }
 
 // ---- staged, persistent projection kernels ----------------------------------------------------------------------
-// A CTA walks tiles of PRJ_TILE consecutive Gaussians.  The inputs of a tile are CONTIGUOUS spans of the attribute
-// arrays (xyz 12 B, scale 12 B, quaternion 16 B -- or cov3D 24 B --, opacity 4 B, features 8 B per Gaussian), so one
-// elected thread moves them into shared memory with 1-D bulk copies (TMA, cp.async.bulk) that complete on an
-// mbarrier, two tiles deep: the copy of tile i + 1 is in flight while tile i is projected, and every global read is a
-// full-line burst instead of the stride-3 / stride-4 scalar loads of a thread-per-Gaussian AoS read (the reference's
-// pattern, fwd.cu:298-316).  Shared-memory reads are conflict-free (stride 3 words is odd; quaternions as LDS.128).
-// Bulk copies need 16-byte aligned addresses and sizes: the < 16 B tail of a partial last tile is copied by the
-// elected thread, and arrays that are not 16-byte aligned fall back to cooperative coalesced loads into the same
-// staging layout (use_tma = 0).
-#define PRJ_TILE 256
-#define PRJ_STAGES 2
+// Every WARP walks tiles of PRJ_TILE = 32 consecutive Gaussians by itself.  The inputs of a tile are CONTIGUOUS spans
+// of the attribute arrays (xyz 12 B, scale 12 B, quaternion 16 B -- or cov3D 24 B --, opacity 4 B, features 8 B per
+// Gaussian), so lane 0 moves them into the warp's shared-memory ring with 1-D bulk copies (TMA, cp.async.bulk) that
+// complete on an mbarrier, PRJ_STAGES tiles deep: the copies of the next tiles are in flight while a tile is projected,
+// and every global read is a full-line burst instead of the stride-3 / stride-4 scalar loads of a thread-per-Gaussian
+// AoS read (the reference's pattern, fwd.cu:298-316).  Shared-memory reads are conflict-free (stride 3 words is odd;
+// quaternions as LDS.128).  Warps never wait for each other: a Gaussian with a huge footprint (hundreds of bins to
+// emit) delays its own warp only -- with CTA-wide tiles every barrier waited for the slowest of eight warps (14 % of
+// the kernel's stall samples).  Bulk copies need 16-byte aligned addresses and sizes: the < 16 B tail of a partial
+// last tile is copied by lane 0, and arrays that are not 16-byte aligned fall back to coalesced loads by the warp into
+// the same staging layout (use_tma = 0).
+#define PRJ_TILE 32
+#define PRJ_WARPS 8
+#define PRJ_STAGES 3
 struct PrjStage { // byte offsets inside one staging buffer
 	static constexpr int XYZ = 0, SC = XYZ + 12 * PRJ_TILE, ROT = SC + 12 * PRJ_TILE, // cov3D (24 B) overlays SC + ROT
 			     OPA = ROT + 16 * PRJ_TILE, COL = OPA + 4 * PRJ_TILE, BYTES = COL + 8 * PRJ_TILE;
 };
-#define PRJ_HDR 128 // mbarriers
+#define PRJ_HDR (8 * PRJ_STAGES * PRJ_WARPS) // mbarriers: one per (warp, stage)
 
-// Thread 0: start the copies of `n` Gaussians beginning at `first` into staging buffer `sb`.
+// Lane 0: start the copies of `n` Gaussians beginning at `first` into staging buffer `sb`.
 __device__ __forceinline__ void prj_issue(unsigned char *sb, unsigned bar, size_t first, int n, const float *means3D,
 					  const float *scales, const float *rotations, const float *cov3D_precomp,
 					  const float *opacities, const float *colors)
@@ -224,14 +227,14 @@ __device__ __forceinline__ void prj_issue(unsigned char *sb, unsigned bar, size_
 	bulk(p_xyz, PrjStage::XYZ, 12); bulk(p_sc, PrjStage::SC, e_sc); bulk(p_rot, PrjStage::ROT, 16);
 	bulk(p_opa, PrjStage::OPA, 4); bulk(p_col, PrjStage::COL, 8);
 }
-// use_tma = 0: the same staging layout filled by all threads with coalesced loads
+// use_tma = 0: the same staging layout filled by the warp with coalesced loads
 __device__ __forceinline__ void prj_coop_fill(unsigned char *sb, size_t first, int n, const float *means3D, const float *scales,
 					      const float *rotations, const float *cov3D_precomp, const float *opacities,
 					      const float *colors)
 {
 	auto fill = [&](const float *src, int offb, int words) {
 		float *dst = reinterpret_cast<float *>(sb + offb);
-		for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+		for (int i = threadIdx.x & 31; i < words; i += 32) dst[i] = src[i];
 	};
 	fill(means3D + 3 * first, PrjStage::XYZ, 3 * n);
 	if (cov3D_precomp) fill(cov3D_precomp + 6 * first, PrjStage::SC, 6 * n);
@@ -241,7 +244,7 @@ __device__ __forceinline__ void prj_coop_fill(unsigned char *sb, size_t first, i
 }
 
 template <bool FILTER>
-__global__ void __launch_bounds__(PRJ_TILE, 4)
+__global__ void __launch_bounds__(PRJ_WARPS * 32, 4)
 project_kernel(int P, int use_tma, const float *__restrict__ means3D, const float *__restrict__ scales, float mod,
 	       const float *__restrict__ rotations, const float *__restrict__ cov3D_precomp,
 	       const float *__restrict__ opacities, const float *__restrict__ colors,
@@ -252,21 +255,22 @@ project_kernel(int P, int use_tma, const float *__restrict__ means3D, const floa
 	       FrameTotals *__restrict__ totals)
 {
 	extern __shared__ __align__(128) unsigned char psm[];
-	const unsigned bar0 = lgs_smem_addr(psm);
-	unsigned char *stage0 = psm + PRJ_HDR;
-	float *stab = reinterpret_cast<float *>(stage0 + PRJ_STAGES * PrjStage::BYTES);
-	const int tid = threadIdx.x;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const unsigned bar0 = lgs_smem_addr(psm) + 8u * PRJ_STAGES * warp; // this warp's mbarriers
+	unsigned char *stage0 = psm + PRJ_HDR + (size_t)warp * PRJ_STAGES * PrjStage::BYTES;
+	float *stab = reinterpret_cast<float *>(psm + PRJ_HDR + (size_t)PRJ_WARPS * PRJ_STAGES * PrjStage::BYTES);
 	const int ntiles = (P + PRJ_TILE - 1) / PRJ_TILE;
-	if (tid == 0 && use_tma) {
+	const int wstride = gridDim.x * PRJ_WARPS, wfirst = blockIdx.x * PRJ_WARPS + warp; // this warp's tiles: wfirst, + wstride, ...
+	if (lane == 0 && use_tma) {
 #pragma unroll
 		for (int s = 0; s < PRJ_STAGES; s++) lgs_mbar_init(bar0 + 8 * s, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	__syncthreads();
-	if (tid == 0 && use_tma) {
+	__syncwarp();
+	if (lane == 0 && use_tma) {
 #pragma unroll
 		for (int s = 0; s < PRJ_STAGES; s++) {
-			const int t = blockIdx.x + s * gridDim.x;
+			const int t = wfirst + s * wstride;
 			if (t < ntiles)
 				prj_issue(stage0 + s * PrjStage::BYTES, bar0 + 8 * s, (size_t)t * PRJ_TILE, min(PRJ_TILE, P - t * PRJ_TILE),
 					  means3D, scales, rotations, cov3D_precomp, opacities, colors);
@@ -274,12 +278,12 @@ project_kernel(int P, int use_tma, const float *__restrict__ means3D, const floa
 	}
 	const float *bt, *tt;
 	float tanW;
-	load_beam_tables(beams, H, W, stab, stab + H, bt, tt, tanW); // (ends with a CTA barrier when the tables fit)
+	load_beam_tables(beams, H, W, stab, stab + H, bt, tt, tanW); // (the kernel's only CTA barrier, when the tables fit)
 
-	unsigned long long t64 = 0; // block-level totals, flushed once per CTA
+	unsigned long long t64 = 0; // totals, flushed once per warp
 	unsigned vis = 0;
 	int it = 0;
-	for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+	for (int tile = wfirst; tile < ntiles; tile += wstride, it++) {
 		const int s = it % PRJ_STAGES;
 		unsigned char *sb = stage0 + s * PrjStage::BYTES;
 		const size_t first = (size_t)tile * PRJ_TILE;
@@ -287,35 +291,35 @@ project_kernel(int P, int use_tma, const float *__restrict__ means3D, const floa
 		if (use_tma) lgs_mbar_wait(bar0 + 8 * s, (unsigned)(it / PRJ_STAGES) & 1u);
 		else {
 			prj_coop_fill(sb, first, n, means3D, scales, rotations, cov3D_precomp, opacities, colors);
-			__syncthreads();
+			__syncwarp();
 		}
-		// ---- this thread's Gaussian: shared memory -> registers ----
-		const bool have = tid < n;
-		const int idx = (int)first + tid;
+		// ---- this lane's Gaussian: shared memory -> registers ----
+		const bool have = lane < n;
+		const int idx = (int)first + lane;
 		float px = 0.f, py = 0.f, pz = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f, o = 0.f;
 		float4 rq = make_float4(0.f, 0.f, 0.f, 0.f);
 		float2 f = make_float2(0.f, 0.f);
 		float cov[6];
 		if (have) {
-			const float *sx = reinterpret_cast<const float *>(sb + PrjStage::XYZ) + 3 * tid;
+			const float *sx = reinterpret_cast<const float *>(sb + PrjStage::XYZ) + 3 * lane;
 			px = sx[0]; py = sx[1]; pz = sx[2];
 			if (cov3D_precomp) {
-				const float2 *sc = reinterpret_cast<const float2 *>(sb + PrjStage::SC) + 3 * tid;
+				const float2 *sc = reinterpret_cast<const float2 *>(sb + PrjStage::SC) + 3 * lane;
 				const float2 c0 = sc[0], c1 = sc[1], c2 = sc[2];
 				cov[0] = c0.x; cov[1] = c0.y; cov[2] = c1.x; cov[3] = c1.y; cov[4] = c2.x; cov[5] = c2.y;
 			} else {
-				const float *ss = reinterpret_cast<const float *>(sb + PrjStage::SC) + 3 * tid;
+				const float *ss = reinterpret_cast<const float *>(sb + PrjStage::SC) + 3 * lane;
 				s0 = ss[0]; s1 = ss[1]; s2 = ss[2];
-				rq = reinterpret_cast<const float4 *>(sb + PrjStage::ROT)[tid];
+				rq = reinterpret_cast<const float4 *>(sb + PrjStage::ROT)[lane];
 			}
 			if (!FILTER) {
-				o = reinterpret_cast<const float *>(sb + PrjStage::OPA)[tid];
-				f = reinterpret_cast<const float2 *>(sb + PrjStage::COL)[tid];
+				o = reinterpret_cast<const float *>(sb + PrjStage::OPA)[lane];
+				f = reinterpret_cast<const float2 *>(sb + PrjStage::COL)[lane];
 			}
 		}
-		__syncthreads(); // every thread has read its inputs: the buffer can take the tile after next
-		if (tid == 0 && use_tma) {
-			const int t = tile + PRJ_STAGES * gridDim.x;
+		__syncwarp(); // every lane has read its inputs: the buffer can take the tile PRJ_STAGES further on
+		if (lane == 0 && use_tma) {
+			const int t = tile + PRJ_STAGES * wstride;
 			if (t < ntiles)
 				prj_issue(sb, bar0 + 8 * s, (size_t)t * PRJ_TILE, min(PRJ_TILE, P - t * PRJ_TILE), means3D, scales, rotations,
 					  cov3D_precomp, opacities, colors);
@@ -366,13 +370,13 @@ project_kernel(int P, int use_tma, const float *__restrict__ means3D, const floa
 						   __float_as_uint(pj.depth), soff)
 				      : make_uint4(0, 0, 0, 0);
 	}
-	if constexpr (!FILTER) { // totals: one atomic pair per warp and CTA lifetime
+	if constexpr (!FILTER) { // totals: one atomic pair per warp lifetime
 #pragma unroll
 		for (int o = 16; o > 0; o >>= 1) {
 			t64 += __shfl_xor_sync(0xffffffffu, t64, o);
 			vis += __shfl_xor_sync(0xffffffffu, vis, o);
 		}
-		if ((tid & 31) == 0 && vis) {
+		if (lane == 0 && vis) {
 			atomicAdd(&totals->num_rendered, t64);
 			atomicAdd(&totals->num_visible, vis);
 		}
@@ -393,7 +397,7 @@ mark_visible_kernel(int P, const float *__restrict__ pts, const float *__restric
 
 namespace {
 inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-inline size_t prj_smem(int H) { return PRJ_HDR + PRJ_STAGES * (size_t)PrjStage::BYTES + (H <= LGS_MAX_SMEM_ROWS ? 8 * (size_t)H : 0); }
+inline size_t prj_smem(int H) { return PRJ_HDR + (size_t)PRJ_WARPS * PRJ_STAGES * PrjStage::BYTES + (H <= LGS_MAX_SMEM_ROWS ? 8 * (size_t)H : 0); }
 inline int prj_grid(int P)
 {
 	static int sms = 0;
@@ -403,8 +407,8 @@ inline int prj_grid(int P)
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 		if (sms <= 0) sms = 148;
 	}
-	const int ntiles = (P + PRJ_TILE - 1) / PRJ_TILE;
-	return ntiles < 4 * sms ? ntiles : 4 * sms; // persistent: four resident CTAs per SM walk the tiles
+	const int nctas = ((P + PRJ_TILE - 1) / PRJ_TILE + PRJ_WARPS - 1) / PRJ_WARPS;
+	return nctas < 4 * sms ? nctas : 4 * sms; // persistent: four resident CTAs per SM, every warp walks its own tiles
 }
 } // namespace
 
@@ -417,7 +421,7 @@ void lgs_launch_project(const FrameGeom &g, const float *means3D, const float *s
 			    (cov3D_precomp ? al16(cov3D_precomp) : (al16(scales) && al16(rotations)));
 	const size_t smem = prj_smem(g.H);
 	cudaFuncSetAttribute(project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	project_kernel<false><<<prj_grid(g.P), PRJ_TILE, smem, st>>>(g.P, use_tma, means3D, scales, mod, rotations, cov3D_precomp,
+	project_kernel<false><<<prj_grid(g.P), PRJ_WARPS * 32, smem, st>>>(g.P, use_tma, means3D, scales, mod, rotations, cov3D_precomp,
 								     opacities, colors, view, g.W, g.H, beams, far_, near_, g.gx, g.RB,
 								     gp.rec, gp.aux, radii, radii_xy, gp.cnt, ranks, capacity, gp.totals);
 }
@@ -430,7 +434,7 @@ void lgs_launch_filter(int P, const float *means3D, const float *scales, float m
 	const int use_tma = al16(means3D) && (cov3D_precomp ? al16(cov3D_precomp) : (al16(scales) && al16(rotations)));
 	const size_t smem = prj_smem(H);
 	cudaFuncSetAttribute(project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	project_kernel<true><<<prj_grid(P), PRJ_TILE, smem, st>>>(P, use_tma, means3D, scales, mod, rotations, cov3D_precomp, nullptr,
+	project_kernel<true><<<prj_grid(P), PRJ_WARPS * 32, smem, st>>>(P, use_tma, means3D, scales, mod, rotations, cov3D_precomp, nullptr,
 								  nullptr, view, W, H, beams, far_, near_, gx, 1, nullptr, nullptr, radii,
 								  radii_xy, nullptr, nullptr, 0u, nullptr);
 }
