@@ -518,6 +518,9 @@ def main():
                     help="N > 1: peer = fused pack + pull over NVLink peer memory (default); sparse = NCCL all-gather of the "
                          "packed rows; dense = NCCL all-reduce of the 13P-float bucket")
     ap.add_argument("--dense-allreduce", action="store_true", help="same as --exchange dense")
+    ap.add_argument("--serial-exchange", action="store_true",
+                    help="N > 1: run the exchange on the frame's own stream instead of a side stream (by default the exchange of "
+                         "step k overlaps filter + forward of step k + 1 and is waited for before that step's backward rewrites the bucket)")
     ap.add_argument("--no-workloads", action="store_true", help="skip extra.workloads (other configs / poses, each vs the reference CUDA)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-dense-grads", action="store_true",
@@ -588,10 +591,18 @@ def main():
         if xmode == "sparse":
             xchg = dp.SparseExchange(P, dev)
 
+    overlap = world > 1 and not args.serial_exchange
+    cur = torch.cuda.current_stream(dev)
+    xs = torch.cuda.Stream(dev) if overlap else None
+    ev_bwd, ev_x = torch.cuda.Event(), torch.cuda.Event()
+    ev_x.record(cur)
+
     def render():
         capi.visible_filter(a_means, a_scales3, a_rots, d["viewmatrix"], d["beams"], H, W, sc["far"], sc["near"])
         fr.forward(d["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"], d["viewmatrix"],
                    d["beams"], H, W, sc["far"], sc["near"], out=out)
+        if overlap:
+            cur.wait_event(ev_x)  # the previous step's exchange is done with the bucket this backward rewrites
         fr.backward(d["g_color"], d["g_depth"], d["g_occ"], grads=grads)
 
     def exchange():
@@ -604,15 +615,33 @@ def main():
 
     def step(timed=False):
         if timed:
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             e[0].record()
         render()
         if timed:
             e[1].record()
-        exchange()
+        if overlap:
+            ev_bwd.record(cur)
+            with torch.cuda.stream(xs):
+                xs.wait_event(ev_bwd)
+                if timed:
+                    e[2].record()
+                exchange()
+                if timed:
+                    e[3].record()
+                ev_x.record(xs)
+        else:
+            if timed:
+                e[2].record()
+            exchange()
+            if timed:
+                e[3].record()
         if timed:
-            e[2].record()
             ev.append(e)
+
+    def drain():
+        if overlap:
+            cur.wait_event(ev_x)  # the last exchange belongs to the timed region
 
     if xchg is not None:  # once, before anything is timed: the sparse exchange must equal the dense all-reduce
         render()
@@ -639,6 +668,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
+    drain()
     e1.record()
     barrier()
     wall = time.time() - t0
@@ -663,8 +693,8 @@ def main():
     value = world * 1e3 / ms_per_step
     R, V, Ninst = fr.num_rendered, int((out["radii"] > 0).sum().item()), fr.num_instances
     # per rank: the local frame (filter + forward + backward) and the exchange (which includes waiting for slower ranks)
-    f_ms = np.array([e[0].elapsed_time(e[1]) for e in ev]); x_ms = np.array([e[1].elapsed_time(e[2]) for e in ev])
-    s_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
+    f_ms = np.array([e[0].elapsed_time(e[1]) for e in ev]); x_ms = np.array([e[2].elapsed_time(e[3]) for e in ev])
+    s_ms = np.array([a_[0].elapsed_time(b_[0]) for a_, b_ in zip(ev[:-1], ev[1:])])  # start of a step to the start of the next
     mine = [float(f_ms.mean()), float(x_ms.mean()), float(np.percentile(s_ms, 10)), float(np.median(s_ms)), float(np.percentile(s_ms, 90))]
     if world > 1:
         allr = [None] * world
@@ -887,6 +917,9 @@ def main():
              "stages": per, "frame_model_bytes": frame_bytes,
              "frame_model_note": "SURVEY 8d byte model of the reference's full-sort algorithm -- NOT traffic this implementation moves",
              "per_rank": per_rank, "exchange": xmode if world > 1 else None,
+             "exchange_overlap": ("side stream: the exchange of step k runs beside filter + forward of step k + 1 and is waited for before "
+                                  "that step's backward rewrites the gradient bucket; the last exchange is inside the timed region")
+             if overlap else ("same stream" if world > 1 else None),
              "step_ms": {"p10": per_rank[0]["step_ms_p10"], "median": per_rank[0]["step_ms_median"], "p90": per_rank[0]["step_ms_p90"]},
              "instrumented_steps": nstage,  # stages / step_ms / per_rank come from these (per-stage events cost ~0.05 ms a step)
              "wall_s": wall}

@@ -175,6 +175,7 @@ __global__ void peer_publish_kernel(PeerHeader *mine, unsigned step)
 	st_release_sys(&mine->ready, step + 1u);
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 peer_pull_kernel(int P, int nranks, int my_rank, char *const *__restrict__ peers, size_t slot_off, int cap, unsigned step,
 		 float *__restrict__ d_means3D, float *__restrict__ d_scales, float *__restrict__ d_rot, float *__restrict__ d_opac,
@@ -200,19 +201,36 @@ peer_pull_kernel(int P, int nranks, int my_rank, char *const *__restrict__ peers
 		if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&status[0], 1u);
 		return;
 	}
-	for (int k = 1; k < nranks; k++) {
-		const int r = (my_rank + k) % nranks; // every rank starts with a different peer
-		const float4 *buf = reinterpret_cast<const float4 *>(peers[r] + slot_off);
-		const unsigned n = s_rows[r];
-		if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&status[1], n);
-		for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-			const float4 *row = buf + 4 * ((size_t)i + 1);
-			const float4 a = __ldcv(row), b = __ldcv(row + 1), c = __ldcv(row + 2), d = __ldcv(row + 3); // peer memory: never from a stale L1 line
-			const unsigned id = __float_as_uint(a.x);
-			if (id >= (unsigned)P) continue;
-			atomicAdd(d_means3D + 3 * (size_t)id, a.y); atomicAdd(d_means3D + 3 * (size_t)id + 1, a.z); atomicAdd(d_means3D + 3 * (size_t)id + 2, a.w);
-			atomicAdd(d_scales + 3 * (size_t)id, b.x); atomicAdd(d_scales + 3 * (size_t)id + 1, b.y); atomicAdd(d_scales + 3 * (size_t)id + 2, b.z);
-			atomicAdd(d_opac + id, b.w);
+	// all peers' rows as ONE index space (prefix over the peers, own rank skipped): every thread has loads from several
+	// peers in flight at once instead of walking the peers one after the other
+	__shared__ unsigned s_start[65];
+	if (threadIdx.x == 0) {
+		unsigned run = 0, mx = 0;
+		for (int k = 0; k < nranks; k++) {
+			s_start[k] = run;
+			if (k != my_rank) run += s_rows[k];
+			mx = max(mx, s_rows[k]);
+		}
+		s_start[nranks] = run;
+		if (blockIdx.x == 0) atomicMax(&status[1], mx);
+	}
+	__syncthreads();
+	const unsigned total = s_start[nranks];
+	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+		int r = 0;
+		while (t >= s_start[r + 1]) r++; // (s_start[r + 1] == s_start[r] for the own rank: never selected)
+		const float4 *row = reinterpret_cast<const float4 *>(peers[r] + slot_off) + 4 * ((size_t)(t - s_start[r]) + 1);
+		const float4 a = __ldcv(row), b = __ldcv(row + 1), c = __ldcv(row + 2), d = __ldcv(row + 3); // peer memory: never from a stale L1 line
+		const unsigned id = __float_as_uint(a.x);
+		if (id >= (unsigned)P) continue;
+		// several ranks may touch the same Gaussian: reductions in L2 (rows of ONE rank are unique, so contention is at most nranks - 1)
+		atomicAdd(d_means3D + 3 * (size_t)id, a.y); atomicAdd(d_means3D + 3 * (size_t)id + 1, a.z); atomicAdd(d_means3D + 3 * (size_t)id + 2, a.w);
+		atomicAdd(d_scales + 3 * (size_t)id, b.x); atomicAdd(d_scales + 3 * (size_t)id + 1, b.y); atomicAdd(d_scales + 3 * (size_t)id + 2, b.z);
+		atomicAdd(d_opac + id, b.w);
+		if (VEC) { // rotation rows 16-byte aligned, colour rows 8-byte aligned (checked by the host): one vector reduction each
+			asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d_rot + 4 * (size_t)id), "f"(c.x), "f"(c.y), "f"(c.z), "f"(c.w) : "memory");
+			asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d_colors + 2 * (size_t)id), "f"(d.x), "f"(d.y) : "memory");
+		} else {
 			atomicAdd(d_rot + 4 * (size_t)id, c.x); atomicAdd(d_rot + 4 * (size_t)id + 1, c.y);
 			atomicAdd(d_rot + 4 * (size_t)id + 2, c.z); atomicAdd(d_rot + 4 * (size_t)id + 3, c.w);
 			atomicAdd(d_colors + 2 * (size_t)id, d.x); atomicAdd(d_colors + 2 * (size_t)id + 1, d.y);
@@ -277,8 +295,13 @@ int lgs_peer_pull(int P, int nranks, int my_rank, void *const *peer_buffers_dev,
 	    !dL_dscale || !dL_drot || !dL_dopacity || !dL_dcolor || !status_dev)
 		return LGS_EINVAL;
 	const size_t slot_off = (size_t)(step & 1u) * (((size_t)cap + 1) * 64);
-	peer_pull_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(P, nranks, my_rank, (char *const *)peer_buffers_dev, slot_off, cap, step,
-								 dL_dmean3D, dL_dscale, dL_drot, dL_dopacity, dL_dcolor, status_dev);
+	const bool vec = (reinterpret_cast<uintptr_t>(dL_drot) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dL_dcolor) & 7u) == 0;
+	if (vec)
+		peer_pull_kernel<true><<<148 * 4, 256, 0, (cudaStream_t)stream>>>(P, nranks, my_rank, (char *const *)peer_buffers_dev, slot_off, cap,
+										  step, dL_dmean3D, dL_dscale, dL_drot, dL_dopacity, dL_dcolor, status_dev);
+	else
+		peer_pull_kernel<false><<<148 * 4, 256, 0, (cudaStream_t)stream>>>(P, nranks, my_rank, (char *const *)peer_buffers_dev, slot_off, cap,
+										   step, dL_dmean3D, dL_dscale, dL_drot, dL_dopacity, dL_dcolor, status_dev);
 	return cudaGetLastError() == cudaSuccess ? 0 : LGS_ECUDA;
 }
 } // extern "C"
