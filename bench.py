@@ -522,6 +522,7 @@ def main():
                     help="N > 1: run the exchange on the frame's own stream instead of a side stream (by default the exchange of "
                          "step k overlaps filter + forward of step k + 1 and is waited for before that step's backward rewrites the bucket)")
     ap.add_argument("--no-workloads", action="store_true", help="skip extra.workloads (other configs / poses, each vs the reference CUDA)")
+    ap.add_argument("--forward-mode", type=int, default=None, help="lgs_set_forward_split(mode): 0 one pipelined kernel, 1 split, 2 evaluate/blend warps")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-dense-grads", action="store_true",
                     help="end-to-end leg copies the dense gradient arrays to the host instead of the non-zero rows")
@@ -551,6 +552,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     L = capi.load()
     L.lgs_set_rows_per_bin(args.rows_per_bin)
+    if args.forward_mode is not None:
+        L.lgs_set_forward_split(args.forward_mode)
 
     sc = synth.make_config(CFG)
     sc["viewmatrix"] = rank_pose(sc, rank if args.pose_rank is None else args.pose_rank)

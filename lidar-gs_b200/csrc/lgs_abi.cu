@@ -183,7 +183,7 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 		g_timer.begin(LGS_STAGE_RENDER_FWD, st);
 		render(entries);
 		g_timer.end(st);
-		g_launches += g_fwd_split.load() && path == 0 ? 7 : 5; // project, 2 x scan, scatter, compositing (1 or 3 launches)
+		g_launches += g_fwd_split.load() == 1 && path == 0 ? 7 : 5; // project, 2 x scan, scatter, compositing (1 or 3 launches)
 		CK(cudaGetLastError());
 		// the scan kernel stored the totals straight into mapped host memory (a memcpy would queue behind whatever bulk
 		// device-to-host transfer the application has in flight on the copy engine); scatter + render keep running
@@ -522,9 +522,10 @@ int lgs_set_sort_all(int on)
 	g_sort_all.store(on ? 1 : 0);
 	return 0;
 }
-int lgs_set_forward_split(int on)
+int lgs_set_forward_split(int mode)
 {
-	g_fwd_split.store(on ? 1 : 0);
+	if (mode < 0 || mode > 2) return fail(LGS_EINVAL, "lgs_set_forward_split: mode must be 0, 1 or 2");
+	g_fwd_split.store(mode);
 	return 0;
 }
 int lgs_timing_enable(int on)
