@@ -698,13 +698,14 @@ def main():
     # per rank: the local frame (filter + forward + backward) and the exchange (which includes waiting for slower ranks)
     f_ms = np.array([e[0].elapsed_time(e[1]) for e in ev]); x_ms = np.array([e[2].elapsed_time(e[3]) for e in ev])
     s_ms = np.array([a_[0].elapsed_time(b_[0]) for a_, b_ in zip(ev[:-1], ev[1:])])  # start of a step to the start of the next
-    mine = [float(f_ms.mean()), float(x_ms.mean()), float(np.percentile(s_ms, 10)), float(np.median(s_ms)), float(np.percentile(s_ms, 90))]
+    mine = [float(f_ms.mean()), float(x_ms.mean()), float(np.percentile(s_ms, 10)), float(np.median(s_ms)), float(np.percentile(s_ms, 90)),
+            int(L.lgs_last_forward_mode())]
     if world > 1:
         allr = [None] * world
         dist.all_gather_object(allr, mine)
     else:
         allr = [mine]
-    per_rank = [dict(rank=r, frame_ms=a[0], exchange_ms=a[1], step_ms_p10=a[2], step_ms_median=a[3], step_ms_p90=a[4])
+    per_rank = [dict(rank=r, frame_ms=a[0], exchange_ms=a[1], step_ms_p10=a[2], step_ms_median=a[3], step_ms_p90=a[4], forward_mode=a[5])
                 for r, a in enumerate(allr)]
     # Gaussians the backward pass of THIS rank visited (the library's own list), read before anything overwrites the scratch
     import ctypes as _C
@@ -919,6 +920,8 @@ def main():
     extra = {"num_rendered": R, "num_visible": V, "num_instances": Ninst, "consumed": cons,
              "stages": per, "frame_model_bytes": frame_bytes,
              "frame_model_note": "SURVEY 8d byte model of the reference's full-sort algorithm -- NOT traffic this implementation moves",
+             "longest_walk_chunks": int(L.lgs_last_longest_walk()),
+             "forward_mode": int(L.lgs_last_forward_mode()),  # 0: worker warp per 2 pixel rows, 3: per row (automatic)
              "per_rank": per_rank, "exchange": xmode if world > 1 else None,
              "exchange_overlap": ("side stream: the exchange of step k runs beside filter + forward of step k + 1 and is waited for before "
                                   "that step's backward rewrites the gradient bucket; the last exchange is inside the timed region")

@@ -358,9 +358,20 @@ int lgs_adam_step(int ntensors, const lgs_adam_tensor *tensors, void *stream);
 int lgs_set_rows_per_bin(int rows);
 /* 1 = sort every list completely in forward (tests); 0 = sort only what compositing consumes. */
 int lgs_set_sort_all(int on);
-/* 1 = forward compositing as three launches (prefix sort, independent pixel-group warps, tail); 0 = one pipelined
- * launch (default, faster on every workload measured; the split stays as a tested alternative). */
-int lgs_set_forward_split(int on);
+/*
+ * Shape of the forward compositing pass (all five produce bit-identical images; tests force each of them):
+ *   -1 automatic (default): one pipelined launch; two-row worker warps, switching to one-row workers while the previous
+ *      frames on the device had pixel groups walking 100 or more chunks of 32 pairs by themselves (rays that never saturate)
+ *    0 one launch, a worker warp per 2 pixel rows          3 one launch, a worker warp per pixel row
+ *    1 three launches (prefix sort, independent pixel-group warps, resumable tail)
+ *    2 one launch, evaluate and blend on separate warps coupled by an mbarrier ring
+ */
+int lgs_set_forward_split(int mode);
+/* The shape (0 .. 3) the last lgs_forward() of this thread actually used. */
+int lgs_last_forward_mode(void);
+/* Longest walk (chunks of 32 (entry, row) pairs, in two-row-worker units) of any pixel group in the frame BEFORE the last
+ * lgs_forward() of this thread: the statistic the automatic mode reads. */
+int lgs_last_longest_walk(void);
 /* Number of (Gaussian, bin) instances materialised by the last lgs_forward() on this thread. */
 long long lgs_last_num_instances(void);
 /*

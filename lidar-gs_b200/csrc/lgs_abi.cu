@@ -17,6 +17,8 @@ namespace {
 thread_local char g_err[512] = "";
 thread_local long long g_last_instances = 0;
 thread_local long long g_overflow_reruns = 0;
+thread_local int g_last_fwd_mode = 0;
+thread_local unsigned g_last_walk = 0;
 // Per (host thread, device) state: mapped pinned host memory the scan kernel writes the frame totals into, the event
 // the host waits on to read them, a side stream for work that is independent of the main dependency chain (zero-fill
 // of the API gradients while the gradient kernel runs; forked from and joined back into the caller's stream with
@@ -28,12 +30,14 @@ struct DevState {
 	cudaStream_t side = nullptr;
 	cudaEvent_t fork = nullptr, join = nullptr;
 	struct Hwm { int P = -1, W = 0, H = 0; long long N = 0; } hwm[2]; // [0] 3-D path, [1] surfel path
+	unsigned *walk_stat = nullptr; // device word: longest walk of the last compositing pass (see FrameTotals::prev_max_chunks)
+	int one_row_workers = 0;       // worker shape the automatic mode currently uses on this device
 };
 #define LGS_MAX_DEVICES 64
 thread_local DevState g_dev[LGS_MAX_DEVICES];
 std::atomic<int> g_rows_per_bin{0};
 std::atomic<int> g_sort_all{0};
-std::atomic<int> g_fwd_split{0};
+std::atomic<int> g_fwd_split{-1}; // -1: automatic worker shape (see bin_and_render)
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_capacity_hint{0}; // test knob: forces the capacity guess of the next frames (0 = automatic)
 
@@ -132,7 +136,8 @@ DevState *dev_state()
 		    (e = cudaEventCreateWithFlags(&ds.scan_done, cudaEventDisableTiming)) != cudaSuccess ||
 		    (e = cudaStreamCreateWithFlags(&ds.side, cudaStreamNonBlocking)) != cudaSuccess ||
 		    (e = cudaEventCreateWithFlags(&ds.fork, cudaEventDisableTiming)) != cudaSuccess ||
-		    (e = cudaEventCreateWithFlags(&ds.join, cudaEventDisableTiming)) != cudaSuccess) {
+		    (e = cudaEventCreateWithFlags(&ds.join, cudaEventDisableTiming)) != cudaSuccess ||
+		    (e = cudaMalloc((void **)&ds.walk_stat, 16)) != cudaSuccess || (e = cudaMemset(ds.walk_stat, 0, 16)) != cudaSuccess) {
 			fail(LGS_ECUDA, "per-device state", e);
 			return nullptr;
 		}
@@ -174,14 +179,14 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 		project(ranks, (unsigned)cap);
 		g_timer.end(st);
 		g_timer.begin(LGS_STAGE_SCAN, st);
-		lgs_launch_scan(g, gp, ds->pinned_dev, (unsigned)cap, st);
+		lgs_launch_scan(g, gp, ds->pinned_dev, (unsigned)cap, path == 0 ? ds->walk_stat : nullptr, st);
 		g_timer.end(st);
 		CK(cudaEventRecord(ds->scan_done, st));
 		g_timer.begin(LGS_STAGE_SCATTER, st);
 		lgs_launch_scatter(g, gp, entries, ranks, (unsigned)cap, far, near, st);
 		g_timer.end(st);
 		g_timer.begin(LGS_STAGE_RENDER_FWD, st);
-		render(entries);
+		render(entries, ds);
 		g_timer.end(st);
 		g_launches += g_fwd_split.load() == 1 && path == 0 ? 7 : 5; // project, 2 x scan, scatter, compositing (1 or 3 launches)
 		CK(cudaGetLastError());
@@ -191,6 +196,15 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 		const unsigned long long N = ds->pinned->num_instances;
 		*R_out = ds->pinned->num_rendered;
 		g_last_instances = (long long)N;
+		if (path == 0) {
+			// Worker shape of the following frames, from the longest walk of the previous frame's compositing pass (it rode in
+			// with the totals): a pixel group that walks hundreds of chunks by itself is the critical path of the whole kernel
+			// (rays that never saturate), and one warp per pixel ROW halves it at ~4 % more work for everybody else.
+			const unsigned w = ds->pinned->prev_max_chunks;
+			g_last_walk = w;
+			if (w >= 100) ds->one_row_workers = 1;      // cfg3: 52 chunks from the centre of the cloud, 120-140 from shifted poses
+			else if (w > 0 && w < 75) ds->one_row_workers = 0;
+		}
 		if (N <= cap) {
 			hw.P = g.P; hw.W = g.W; hw.H = g.H;
 			hw.N = (long long)N;
@@ -255,9 +269,12 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn 
 			lgs_launch_project(g, means3D, scales, scale_modifier, rotations, cov3D_precomp, opacities, colors_precomp,
 					   viewmatrix, beam_inclinations, far, near, gp, radii, radii_xy, ranks, cap, st);
 		},
-		[&](uint4 *entries) {
+		[&](uint4 *entries, DevState *ds) {
+			int mode = g_fwd_split.load();
+			if (mode < 0) mode = ds->one_row_workers ? 3 : 0;
+			g_last_fwd_mode = mode;
 			lgs_launch_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_depth, out_occ,
-					      g_sort_all.load(), g_fwd_split.load(), st);
+					      g_sort_all.load(), mode, ds->walk_stat, st);
 		},
 		&R);
 	if (rc < 0) return rc;
@@ -422,7 +439,7 @@ int lgs_surfel_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_al
 			lgs_launch_surfel_project(g, means3D, scales, scale_modifier, rotations, opacities, colors_precomp, viewmatrix,
 						  beam_inclinations, far, near, gp, radii, radii_xy, ranks, cap, st);
 		},
-		[&](uint4 *entries) {
+		[&](uint4 *entries, DevState *) {
 			lgs_launch_surfel_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_others,
 						     g_sort_all.load(), st);
 		},
@@ -524,7 +541,7 @@ int lgs_set_sort_all(int on)
 }
 int lgs_set_forward_split(int mode)
 {
-	if (mode < 0 || mode > 2) return fail(LGS_EINVAL, "lgs_set_forward_split: mode must be 0, 1 or 2");
+	if (mode < -1 || mode > 3) return fail(LGS_EINVAL, "lgs_set_forward_split: mode must be -1 .. 3");
 	g_fwd_split.store(mode);
 	return 0;
 }
@@ -554,6 +571,8 @@ int lgs_timing_collect(double *ms_per_stage, long long *launches_per_stage)
 }
 long long lgs_last_num_instances(void) { return g_last_instances; }
 long long lgs_overflow_reruns(void) { return g_overflow_reruns; }
+int lgs_last_forward_mode(void) { return g_last_fwd_mode; }
+int lgs_last_longest_walk(void) { return (int)g_last_walk; }
 int lgs_set_capacity_hint(long long instances)
 {
 	if (instances < 0) return fail(LGS_EINVAL, "lgs_set_capacity_hint: negative capacity");

@@ -45,7 +45,7 @@ scan_bins_kernel(int nbins, uint32_t *__restrict__ cnt, uint32_t *__restrict__ l
 // single block: exclusive scan of the per-bin totals (in place: binbase[b] holds total on entry)
 __global__ void __launch_bounds__(1024)
 scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__restrict__ totals, uint32_t *__restrict__ order,
-		  FrameTotals *__restrict__ host_totals, unsigned capacity)
+		  FrameTotals *__restrict__ host_totals, unsigned capacity, unsigned *__restrict__ walk_stat)
 {
 	__shared__ unsigned wsum[32];
 	__shared__ unsigned carry_s;
@@ -76,6 +76,10 @@ scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__rest
 		// the binning buffer was sized from a high-water mark before the count was known: if it is too small, every
 		// later kernel of the frame returns at once (they test this flag) and the host re-runs the frame
 		totals->overflow = carry_s > capacity ? 1u : 0u;
+		if (walk_stat) { // left there by the previous frame's compositing kernel (same stream: it has completed)
+			totals->prev_max_chunks = *walk_stat;
+			*walk_stat = 0u;
+		}
 		if (host_totals) { // mapped pinned host memory: the host reads the counts after waiting for an event, no copy engine involved
 			FrameTotals t = *totals;
 			t.num_instances = carry_s;
@@ -163,11 +167,12 @@ scatter_kernel(int P, int gx, int RB, int far_, int near_, const uint4 *__restri
 
 } // namespace
 
-void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, unsigned capacity, cudaStream_t st)
+void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, unsigned capacity, unsigned *walk_stat,
+		     cudaStream_t st)
 {
 	int warps_per_block = 8;
 	scan_bins_kernel<<<(g.nbins + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(g.nbins, gp.cnt, gp.loc, gp.binbase);
-	scan_total_kernel<<<1, 1024, 0, st>>>(g.nbins, gp.binbase, gp.totals, gp.order, host_totals, capacity);
+	scan_total_kernel<<<1, 1024, 0, st>>>(g.nbins, gp.binbase, gp.totals, gp.order, host_totals, capacity, walk_stat);
 }
 
 void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, const uint32_t *ranks, unsigned capacity,

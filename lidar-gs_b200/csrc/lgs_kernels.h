@@ -15,14 +15,15 @@ void lgs_launch_filter(int P, const float *means3D, const float *scales, float m
 void lgs_launch_mark_visible(int P, const float *means3D, const float *view, unsigned char *present, cudaStream_t st);
 
 // bucket counts -> per-bin exclusive offsets (loc), bin bases (binbase), totals->num_instances / overflow; cnt reset to 0
-void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, unsigned capacity, cudaStream_t st);
+void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, unsigned capacity, unsigned *walk_stat,
+		     cudaStream_t st);
 // (Gaussian, bin) instances -> entries[], bin-major / bucket-minor, unordered inside a bucket; positions from the rank stream
 void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, const uint32_t *ranks, unsigned capacity,
 			int far_, int near_, cudaStream_t st);
 
 void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries,
 			   const float *bg, const float *beams, float *out_color, float *out_depth, float *out_occ,
-			   int sort_all, int split, cudaStream_t st);
+			   int sort_all, int split, unsigned *walk_stat, cudaStream_t st);
 void lgs_launch_render_bwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, const uint4 *entries,
 			   const float *bg, const float *beams, const float *dL_dpix, const float *dL_ddepth,
 			   const float *dL_docc, float *grad, cudaStream_t st);

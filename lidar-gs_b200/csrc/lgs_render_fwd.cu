@@ -69,8 +69,8 @@ struct SortSmem {
 	static constexpr size_t HIST = BVAL + 4 * FWD_CAP;         // NSUB + 1 counters -> sub-bucket starts
 	static constexpr size_t BYTES = (HIST + 4 * (FWD_NSUB + 1) + 15) / 16 * 16;
 };
-template <int RB> struct TailCfg {
-	static constexpr int NPG = RB >= 2 ? RB / 2 : 1;     // 32-pixel groups (2 rows x 16 columns) = worker warps
+template <int RB, int ROWS = 2> struct TailCfg {
+	static constexpr int NPG = RB >= ROWS ? RB / ROWS : 1; // worker warps: one per ROWS rows x 16 columns of the bin
 	static constexpr int NW = NPG + 1;                    // + the sorter warp (last)
 	static constexpr int NT = NW * 32;
 	static constexpr size_t O_BAR = 0;                                   // full[NSLOT], empty[NSLOT] mbarriers
@@ -324,7 +324,7 @@ struct GroupWorker {
 	// shared memory of this warp
 	float *tile; float4 *pf; float4 *sray; unsigned *pmask; uint2 *queue;
 	// identity
-	int lane, hrow, pcol, grp, row0, px, py;
+	int lane, hrow, pcol, grp, rowbase, row0, px, py; // rowbase: first row of this worker inside the bin
 	unsigned lt;
 	bool inside;
 	const float4 *rec;
@@ -339,7 +339,7 @@ struct GroupWorker {
 	uint2 ppair;
 	float4 pq0, pq1, pq2, pq3;
 
-	__device__ __forceinline__ void init(unsigned char *wb, const FrameGeom &g, int RB, int bin, int grp_, int lane_,
+	__device__ __forceinline__ void init(unsigned char *wb, const FrameGeom &g, int RB, int rows, int bin, int grp_, int lane_,
 					     const float *__restrict__ beams, const float4 *rec_, uint4 *ebin_, bool resume,
 					     const float *final_T, const uint32_t *n_contrib, const float4 *fin)
 	{
@@ -351,9 +351,10 @@ struct GroupWorker {
 		lane = lane_; grp = grp_; rec = rec_; ebin = ebin_;
 		hrow = lane >> 4; pcol = lane & 15;
 		const int tx = bin % g.gx, rg = bin / g.gx;
-		px = tx * LGS_TILE_X_ + pcol; py = rg * RB + 2 * grp + hrow;
-		inside = px < g.W && py < g.H && 2 * grp + hrow < RB;
-		row0 = rg * RB + 2 * grp;
+		rowbase = rows * grp; // a one-row worker (rows = 1) uses lanes 0..15 only
+		px = tx * LGS_TILE_X_ + pcol; py = rg * RB + rowbase + hrow;
+		inside = px < g.W && py < g.H && hrow < rows && rowbase + hrow < RB;
+		row0 = rg * RB + rowbase;
 		lt = (1u << lane) - 1u;
 		T = 1.0f; C0 = 0.f; C1 = 0.f; D = 0.f; last = 0; stop = 0;
 		PixelRay ray = {0.f, 0.f, 0.f};
@@ -451,7 +452,7 @@ struct GroupWorker {
 		}
 		// the backward pass skips (entry, row) pairs nothing was blended in: flags ride in the entry's spare word
 		const unsigned bl = __reduce_or_sync(0xffffffffu, blended);
-		if (valid && ((bl >> lane) & 1u)) atomicOr(&ebin[pos].w, 1u << (2 * grp + h));
+		if (valid && ((bl >> lane) & 1u)) atomicOr(&ebin[pos].w, 1u << (rowbase + h)); // bit = row inside the bin
 		live = __ballot_sync(0xffffffffu, !done);
 		nchunks++;
 		__syncwarp(); // tile / pf / pmask are free again
@@ -528,7 +529,7 @@ render_fwd_groups_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 	const unsigned base = binbase[bin], ntotal = binbase[bin + 1] - base, sorted = sorted_end[bin];
 	uint4 *ebin = entries + base;
 	GroupWorker w;
-	w.init(smem + (size_t)warp * WorkSmem::BYTES, g, RB, bin, grp, lane, beams, rec, ebin, false, nullptr, nullptr, nullptr);
+	w.init(smem + (size_t)warp * WorkSmem::BYTES, g, RB, 2, bin, grp, lane, beams, rec, ebin, false, nullptr, nullptr, nullptr);
 	uint4 enext = make_uint4(0u, 0u, 0u, 0u);
 	if ((unsigned)lane < sorted) enext = ebin[lane];
 	for (unsigned j0 = 0; j0 < sorted && w.live; j0 += 32) {
@@ -544,18 +545,18 @@ render_fwd_groups_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 }
 
 // ---- kernel C: the tail of the bins whose rays outlive the sorted prefix --------------------------------------------
-template <int RB>
-__global__ void __launch_bounds__(TailCfg<RB>::NT, RB <= 8 ? 4 : 2)
+template <int RB, int ROWS>
+__global__ void __launch_bounds__(TailCfg<RB, ROWS>::NT, TailCfg<RB, ROWS>::NT <= 160 ? 4 : (TailCfg<RB, ROWS>::NT <= 288 ? 2 : 1))
 render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ loc,
 		       const uint32_t *__restrict__ binbase, uint4 *entries, const float *__restrict__ bg,
 		       const float *__restrict__ beams, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
 		       uint32_t *__restrict__ sorted_end, const uint32_t *__restrict__ alive, float4 *__restrict__ fin,
 		       uint4 *__restrict__ cta_prof, float *__restrict__ out_color, float *__restrict__ out_depth,
 		       float *__restrict__ out_occ, int sort_all, int full, const uint32_t *__restrict__ order,
-		       const FrameTotals *__restrict__ totals)
+		       const FrameTotals *__restrict__ totals, unsigned *__restrict__ walk_stat)
 {
 	if (totals->overflow) return; // binning buffer too small for this frame: the host re-runs it (lgs_abi.cu)
-	using C = TailCfg<RB>;
+	using C = TailCfg<RB, ROWS>;
 	constexpr int NT = C::NT, NPG = C::NPG;
 	// full = 1: this kernel is the whole forward pass (no kernels A / B): every bin starts from scratch, in the launch
 	// order the scan prepared
@@ -623,7 +624,7 @@ render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 	} else {
 		// =============================== worker warp: pixel group `warp`, resumed from kernel B's state ===============
 		GroupWorker w;
-		w.init(smem + C::O_WORK + (size_t)warp * WorkSmem::BYTES, g, RB, bin, warp, lane, beams, rec, entries + base, !full, final_T,
+		w.init(smem + C::O_WORK + (size_t)warp * WorkSmem::BYTES, g, RB, ROWS, bin, warp, lane, beams, rec, entries + base, !full, final_T,
 		       n_contrib, fin);
 		bool gdone = w.live == 0;
 		if (gdone && lane == 0) atomicAdd(&sctl[0], 1u);
@@ -652,7 +653,10 @@ render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 			it++;
 		}
 		if (!gdone) w.flush();
-		if (lane == 0 && w.nchunks) atomicAdd(&sctl[2], w.nchunks);
+		if (lane == 0 && w.nchunks) {
+			atomicAdd(&sctl[2], w.nchunks);
+			if (walk_stat) atomicMax(walk_stat, w.nchunks * (2 / ROWS)); // in two-row-worker units whatever the worker shape
+		}
 		w.store(g, bg, final_T, n_contrib, fin, out_color, out_depth, out_occ);
 	}
 	__syncwarp();
@@ -698,7 +702,7 @@ render_fwd_pipe_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 		       const float *__restrict__ beams, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
 		       uint32_t *__restrict__ sorted_end, float4 *__restrict__ fin, uint4 *__restrict__ cta_prof,
 		       float *__restrict__ out_color, float *__restrict__ out_depth, float *__restrict__ out_occ, int sort_all,
-		       const uint32_t *__restrict__ order, const FrameTotals *__restrict__ totals)
+		       const uint32_t *__restrict__ order, const FrameTotals *__restrict__ totals, unsigned *__restrict__ walk_stat)
 {
 	if (totals->overflow) return;
 	using C = PipeCfg<RB>;
@@ -961,7 +965,10 @@ render_fwd_pipe_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 			__syncwarp();
 			lgs_mbar_arrive(cbar + 16 + 8 * b); // cempty[b]
 		}
-		if (lane == 0 && nchunks) atomicAdd(&sctl[2], nchunks);
+		if (lane == 0 && nchunks) {
+			atomicAdd(&sctl[2], nchunks);
+			if (walk_stat) atomicMax(walk_stat, nchunks);
+		}
 		if (inside) {
 			const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
 			final_T[pix] = T;
@@ -980,7 +987,8 @@ render_fwd_pipe_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 
 template <int RB>
 void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries, const float *bg,
-		const float *beams, float *out_color, float *out_depth, float *out_occ, int sort_all, int split, cudaStream_t st)
+		const float *beams, float *out_color, float *out_depth, float *out_occ, int sort_all, int split, unsigned *walk_stat,
+		cudaStream_t st)
 {
 	using C = TailCfg<RB>;
 	constexpr int NPG = C::NPG;
@@ -989,10 +997,18 @@ void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uin
 		cudaFuncSetAttribute(render_fwd_pipe_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP::BYTES);
 		render_fwd_pipe_kernel<RB><<<g.nbins, CP::NT, CP::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, bg, beams, ip.final_T,
 									       ip.n_contrib, ip.sorted_end, ip.fin, ip.cta_prof, out_color, out_depth,
-									       out_occ, sort_all, gp.order, gp.totals);
+									       out_occ, sort_all, gp.order, gp.totals, walk_stat);
 		return;
 	}
-	cudaFuncSetAttribute(render_fwd_tail_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
+	if (split == 3) { // one worker warp per pixel ROW (twice the warps per bin: shorter critical path, half-empty blend)
+		using C1 = TailCfg<RB, 1>;
+		cudaFuncSetAttribute(render_fwd_tail_kernel<RB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1::BYTES);
+		render_fwd_tail_kernel<RB, 1><<<g.nbins, C1::NT, C1::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, bg, beams, ip.final_T,
+										  ip.n_contrib, ip.sorted_end, ip.alive, ip.fin, ip.cta_prof, out_color,
+										  out_depth, out_occ, sort_all, 1, gp.order, gp.totals, walk_stat);
+		return;
+	}
+	cudaFuncSetAttribute(render_fwd_tail_kernel<RB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
 	if (split) {
 		const size_t smA = FWD_GW * SortSmem::BYTES, smB = FWD_GW * WorkSmem::BYTES;
 		cudaFuncSetAttribute(sort_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
@@ -1002,22 +1018,22 @@ void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uin
 			g, gp.rec, gp.binbase, entries, bg, beams, ip.final_T, ip.n_contrib, ip.sorted_end, ip.alive, ip.fin, out_color,
 			out_depth, out_occ, gp.totals);
 	}
-	render_fwd_tail_kernel<RB><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, bg, beams, ip.final_T,
+	render_fwd_tail_kernel<RB, 2><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, bg, beams, ip.final_T,
 								     ip.n_contrib, ip.sorted_end, ip.alive, ip.fin, ip.cta_prof, out_color,
-								     out_depth, out_occ, sort_all, split ? 0 : 1, gp.order, gp.totals);
+								     out_depth, out_occ, sort_all, split ? 0 : 1, gp.order, gp.totals, walk_stat);
 }
 
 } // namespace
 
 void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries,
 			   const float *bg, const float *beams, float *out_color, float *out_depth, float *out_occ,
-			   int sort_all, int split, cudaStream_t st)
+			   int sort_all, int split, unsigned *walk_stat, cudaStream_t st)
 {
 	switch (g.RB) {
-	case 1: launch_fwd<1>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, st); break;
-	case 2: launch_fwd<2>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, st); break;
-	case 4: launch_fwd<4>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, st); break;
-	case 8: launch_fwd<8>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, st); break;
-	default: launch_fwd<16>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, st); break;
+	case 1: launch_fwd<1>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
+	case 2: launch_fwd<2>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
+	case 4: launch_fwd<4>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
+	case 8: launch_fwd<8>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
+	default: launch_fwd<16>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
 	}
 }

@@ -380,3 +380,34 @@ def test_high_water_mark_follows_a_growing_scene():
     util.run_abi(big)
     assert L.lgs_overflow_reruns() == before, "third frame must fit the high-water mark of the second"
     assert reruns in (0, 1)
+
+
+def test_worker_shape_follows_the_longest_walk():
+    """Automatic forward mode: frames whose rays never saturate (tiny opacities: every pixel group walks its whole list) switch
+    the following frames on the device to one worker warp per pixel row, dense frames switch back; the images do not depend on
+    the shape (bit-identical to the forced modes)."""
+    from lgs_b200 import capi
+    L = capi.load()
+    dense = _scene(40000, 32, 512, 31, pose="identity")     # short lists: no pixel group walks far
+    thin = _scene(400000, 32, 512, 32, pose="identity")     # long lists and rays that never saturate: every group walks them all
+    thin["opacities"] = np.full_like(thin["opacities"], 0.02)
+    L.lgs_set_forward_split(0)
+    ref_thin, _ = util.run_abi(thin, backward=False)
+    ref_dense, _ = util.run_abi(dense, backward=False)
+    L.lgs_set_forward_split(-1)
+    try:
+        modes = []
+        for _ in range(4):
+            res, _ = util.run_abi(thin, backward=False)
+            modes.append(L.lgs_last_forward_mode())
+            for k in ("color", "depth", "occ"):
+                assert np.array_equal(res[k].view(np.uint32), ref_thin[k].view(np.uint32)), k
+        assert modes[-1] == 3, (modes, L.lgs_last_longest_walk())  # the statistic of frame k reaches the host with frame k + 1 and shapes frame k + 2
+        for _ in range(4):
+            res, _ = util.run_abi(dense, backward=False)
+            modes.append(L.lgs_last_forward_mode())
+            for k in ("color", "depth", "occ"):
+                assert np.array_equal(res[k].view(np.uint32), ref_dense[k].view(np.uint32)), k
+        assert modes[-1] == 0, (modes, L.lgs_last_longest_walk())
+    finally:
+        L.lgs_set_forward_split(-1)
