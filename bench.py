@@ -482,7 +482,12 @@ def other_workloads(dev, L, steps=30):
     p7 = dict(sc)
     p7["viewmatrix"] = rank_pose(sc, 7)
     entry("cfg3 from the pose rank 7 renders, fwd+bwd", ours_3d(p7), ref_3d(p7))
-    del sc, lo, p7
+    wall = dict(sc)  # a surface at one range: every bin's list sits in one or two depth buckets of thousands of entries
+    m = sc["means3D"].astype(np.float64)
+    m = m / np.linalg.norm(m, axis=1, keepdims=True) * (30.0 + np.random.default_rng(8).uniform(-0.5, 0.5, (m.shape[0], 1)))
+    wall["means3D"] = np.ascontiguousarray(m, np.float32)
+    entry("cfg3 Gaussians moved onto a 1 m thick shell at 30 m (oversized depth buckets), fwd+bwd", ours_3d(wall), ref_3d(wall))
+    del sc, lo, p7, wall, m
     try:
         ss = synth.make_surfel_config(5)
         d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in ss.items() if isinstance(v, np.ndarray)}

@@ -166,10 +166,14 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 	else cap = 4 * (size_t)g.P + 4096;
 	for (int attempt = 0;; attempt++) {
 		if (cap > 0xfffffff0ull) return fail(LGS_EINVAL, "binning buffer would exceed 2^32 instances");
-		const size_t ranks_off = lgs_al(cap * sizeof(uint4));
+		// 3-D path: sorted lists (offset 0: what the backward pass is handed) | lists as scattered | rank stream = 36 B per
+		// instance; surfel path (sorts in place): lists | rank stream = 20 B per instance
+		const size_t list_bytes = lgs_al(cap * sizeof(uint4));
+		const size_t ranks_off = (path == 0 ? 2 : 1) * list_bytes;
 		char *bb = binning_buffer(ranks_off + cap * sizeof(uint32_t), binning_user);
 		if (!bb) return fail(LGS_ENOMEM, "binning callback returned NULL");
 		uint4 *entries = (uint4 *)bb;
+		uint4 *scattered = path == 0 ? (uint4 *)(bb + list_bytes) : entries;
 		uint32_t *ranks = (uint32_t *)(bb + ranks_off);
 		g_timer.begin(LGS_STAGE_CLEAR, st);
 		CK(cudaMemsetAsync(gp.cnt, 0, (size_t)g.nbins * LGS_NB * 4, st));
@@ -183,10 +187,10 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 		g_timer.end(st);
 		CK(cudaEventRecord(ds->scan_done, st));
 		g_timer.begin(LGS_STAGE_SCATTER, st);
-		lgs_launch_scatter(g, gp, entries, ranks, (unsigned)cap, far, near, st);
+		lgs_launch_scatter(g, gp, scattered, ranks, (unsigned)cap, far, near, st);
 		g_timer.end(st);
 		g_timer.begin(LGS_STAGE_RENDER_FWD, st);
-		render(entries, ds);
+		render(entries, scattered, ds);
 		g_timer.end(st);
 		g_launches += g_fwd_split.load() == 1 && path == 0 ? 7 : 5; // project, 2 x scan, scatter, compositing (1 or 3 launches)
 		CK(cudaGetLastError());
@@ -269,11 +273,11 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn 
 			lgs_launch_project(g, means3D, scales, scale_modifier, rotations, cov3D_precomp, opacities, colors_precomp,
 					   viewmatrix, beam_inclinations, far, near, gp, radii, radii_xy, ranks, cap, st);
 		},
-		[&](uint4 *entries, DevState *ds) {
+		[&](uint4 *entries, uint4 *scattered, DevState *ds) {
 			int mode = g_fwd_split.load();
 			if (mode < 0) mode = ds->one_row_workers ? 3 : 0;
 			g_last_fwd_mode = mode;
-			lgs_launch_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_depth, out_occ,
+			lgs_launch_render_fwd(g, gp, ip, entries, scattered, background, beam_inclinations, out_color, out_depth, out_occ,
 					      g_sort_all.load(), mode, ds->walk_stat, st);
 		},
 		&R);
@@ -439,7 +443,7 @@ int lgs_surfel_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_al
 			lgs_launch_surfel_project(g, means3D, scales, scale_modifier, rotations, opacities, colors_precomp, viewmatrix,
 						  beam_inclinations, far, near, gp, radii, radii_xy, ranks, cap, st);
 		},
-		[&](uint4 *entries, DevState *) {
+		[&](uint4 *entries, uint4 *, DevState *) {
 			lgs_launch_surfel_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_others,
 						     g_sort_all.load(), st);
 		},

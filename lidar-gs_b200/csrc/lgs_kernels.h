@@ -21,7 +21,9 @@ void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_t
 void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, const uint32_t *ranks, unsigned capacity,
 			int far_, int near_, cudaStream_t st);
 
-void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries,
+// entries: the SORTED lists (written lazily by the sorter warps, read by compositing and by the backward pass);
+// unsorted: the lists as the scatter kernel left them (the sorter's input, and its scratch for oversized depth buckets)
+void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries, uint4 *unsorted,
 			   const float *bg, const float *beams, float *out_color, float *out_depth, float *out_occ,
 			   int sort_all, int split, unsigned *walk_stat, cudaStream_t st);
 void lgs_launch_render_bwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, const uint4 *entries,

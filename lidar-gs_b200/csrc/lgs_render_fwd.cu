@@ -67,7 +67,9 @@ struct SortSmem {
 	static constexpr size_t BKEY = RAW + 2 * 16 * FWD_CAP;     // sub-bucketed keys / values
 	static constexpr size_t BVAL = BKEY + 8 * FWD_CAP;
 	static constexpr size_t HIST = BVAL + 4 * FWD_CAP;         // NSUB + 1 counters -> sub-bucket starts
-	static constexpr size_t BYTES = (HIST + 4 * (FWD_NSUB + 1) + 15) / 16 * 16;
+	static constexpr size_t PH1 = (HIST + 4 * (FWD_NSUB + 1) + 15) / 16 * 16; // oversized buckets: sub-range starts, level 1 / level 2
+	static constexpr size_t PH2 = PH1 + 4 * (FWD_NSUB + 4);
+	static constexpr size_t BYTES = (PH2 + 4 * (FWD_NSUB + 4) + 15) / 16 * 16;
 };
 template <int RB, int ROWS = 2> struct TailCfg {
 	static constexpr int NPG = RB >= ROWS ? RB / ROWS : 1; // worker warps: one per ROWS rows x 16 columns of the bin
@@ -207,12 +209,12 @@ __device__ __forceinline__ void warp_sort_segment(uint4 *seg, const uint4 *raw, 
 
 // Segment iterator over a bin's depth buckets (bucket offsets in `sloc`, LGS_NB + 1 entries): the next segment at or
 // behind bucket k is buckets [k, k2), n entries starting at list position s0 (n = 0: none left).
-__device__ __forceinline__ void next_segment(const unsigned *sloc, int k, int &k2, unsigned &s0, unsigned &n)
+__device__ __forceinline__ void next_segment(const unsigned *sloc, int k, int &k2, unsigned &s0, unsigned &n, int NBK = LGS_NB)
 {
 	n = 0; k2 = k; s0 = 0;
-	while (k < LGS_NB) {
+	while (k < NBK) {
 		k2 = k; s0 = sloc[k]; n = 0;
-		while (k2 < LGS_NB) {
+		while (k2 < NBK) {
 			const unsigned c = sloc[k2 + 1] - sloc[k2];
 			if (n > 0 && n + c > FWD_CAP) break;
 			n += c;
@@ -224,13 +226,65 @@ __device__ __forceinline__ void next_segment(const unsigned *sloc, int k, int &k
 	}
 }
 
-// The sorter warp of kernels A and C.  Walks the segments from bucket `k0` on; the raw entries of a (not oversized)
-// segment travel to shared memory as ONE bulk copy issued one segment ahead (it overlaps the sort of the previous
-// one); an oversized bucket is sorted in place in global memory.  `keep_going()` is asked before every segment
-// (laziness); `publish(seg position, chunk offset, count, sorted-from-shared?)` hands a sorted chunk on.  Returns the
-// list position up to which the bin is sorted.
-template <bool SLOT, class KeepGoing, class Acquire, class Publish>
-__device__ __forceinline__ unsigned run_sorter(unsigned char *ss, uint4 *ebin, unsigned ntotal, int k0, int lane,
+// Out-of-place counting partition of n entries by FWD_NSUB linear sub-ranges of their 64-bit key (depth bits << 32 | idx)
+// over the keys' own [min, max]: `out` receives the entries grouped by sub-range (unordered inside), ph[0 .. NSUB] the
+// group starts.  One warp, three passes over the entries; `cur` is FWD_NSUB words of scratch.
+__device__ __forceinline__ void warp_partition_by_key(const uint4 *in, uint4 *out, int n, unsigned *ph, unsigned *cur, int lane)
+{
+	unsigned long long kmin = ~0ull, kmax = 0ull;
+	for (int i = lane; i < n; i += 32) {
+		const uint4 e = in[i];
+		const unsigned long long k = ((unsigned long long)e.x << 32) | e.y;
+		kmin = k < kmin ? k : kmin;
+		kmax = k > kmax ? k : kmax;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		const unsigned long long a = __shfl_xor_sync(0xffffffffu, kmin, o), b = __shfl_xor_sync(0xffffffffu, kmax, o);
+		kmin = a < kmin ? a : kmin;
+		kmax = b > kmax ? b : kmax;
+	}
+	for (int i = lane; i <= FWD_NSUB; i += 32) ph[i] = 0;
+	__syncwarp();
+	const double scale = (double)FWD_NSUB / ((double)(kmax - kmin) + 1.0);
+	// monotone in k: integer -> double rounding, a positive scale and truncation all preserve order
+	auto subof = [&](unsigned long long k) { return min((int)((double)(k - kmin) * scale), FWD_NSUB - 1); };
+	for (int i = lane; i < n; i += 32) {
+		const uint4 e = in[i];
+		atomicAdd(&ph[subof(((unsigned long long)e.x << 32) | e.y)], 1u);
+	}
+	__syncwarp();
+	{
+		constexpr int PER = FWD_NSUB / 32;
+		unsigned v[PER], sum = 0;
+#pragma unroll
+		for (int t = 0; t < PER; t++) { v[t] = ph[lane * PER + t]; sum += v[t]; }
+		unsigned run = warp_excl_scan_u32(sum, lane);
+#pragma unroll
+		for (int t = 0; t < PER; t++) { ph[lane * PER + t] = run; cur[lane * PER + t] = run; run += v[t]; }
+		if (lane == 31) ph[FWD_NSUB] = run;
+	}
+	__syncwarp();
+	for (int i = lane; i < n; i += 32) {
+		const uint4 e = in[i];
+		out[atomicAdd(&cur[subof(((unsigned long long)e.x << 32) | e.y)], 1u)] = e;
+	}
+	__syncwarp(); // (orders the global writes above before this warp's later reads of `out`)
+}
+
+// The sorter warp of kernels A and C.  `ubin` is the bin's list as the scatter kernel left it (bin-major, depth-bucket-
+// minor, unordered inside a bucket), `sbin` the same positions of the SORTED list the compositing and the backward pass
+// read; the sorter never permutes in place.  It walks the segments from bucket `k0` on.  The raw entries of a segment of
+// at most FWD_CAP entries travel to shared memory as ONE bulk copy issued one segment ahead (it overlaps the sort of the
+// previous one).  A single depth bucket with more entries than that (a surface seen at one range fills one bucket of a
+// bin with thousands of Gaussians) is first partitioned through global memory by sub-ranges of its keys -- `ubin` ->
+// `sbin`, and once more `sbin` -> `ubin` for a sub-range that is still too large (e.g. many exactly equal depths: the
+// second level then separates by index) -- after which every group of sub-ranges goes through the ordinary shared-memory
+// sort.  `keep_going(position)` is asked before every segment (laziness; inside an oversized bucket only when
+// LAZY_INSIDE); `acquire_slot()` / `publish(list position, count)` hand a sorted chunk on.  Returns the list position up
+// to which the bin is sorted.
+template <bool SLOT, bool LAZY_INSIDE, class KeepGoing, class Acquire, class Publish>
+__device__ __forceinline__ unsigned run_sorter(unsigned char *ss, uint4 *ubin, uint4 *sbin, unsigned ntotal, int k0, int lane,
 						KeepGoing keep_going, Acquire acquire_slot, Publish publish)
 {
 	const unsigned *sloc = reinterpret_cast<const unsigned *>(ss + SortSmem::LOC);
@@ -238,11 +292,12 @@ __device__ __forceinline__ unsigned run_sorter(unsigned char *ss, uint4 *ebin, u
 	unsigned long long *bkey = reinterpret_cast<unsigned long long *>(ss + SortSmem::BKEY);
 	unsigned *bval = reinterpret_cast<unsigned *>(ss + SortSmem::BVAL);
 	unsigned *hist = reinterpret_cast<unsigned *>(ss + SortSmem::HIST);
+	unsigned *ph1 = reinterpret_cast<unsigned *>(ss + SortSmem::PH1), *ph2 = reinterpret_cast<unsigned *>(ss + SortSmem::PH2);
 	const unsigned bar_raw = lgs_smem_addr(ss + SortSmem::BAR);
 	auto prefetch = [&](unsigned s0, unsigned n, unsigned buf) {
 		if (lane == 0) {
 			lgs_mbar_arrive_expect_tx(bar_raw + 8 * buf, n * 16u);
-			lgs_bulk_g2s(lgs_smem_addr(raw + buf * FWD_CAP), ebin + s0, n * 16u, bar_raw + 8 * buf);
+			lgs_bulk_g2s(lgs_smem_addr(raw + buf * FWD_CAP), ubin + s0, n * 16u, bar_raw + 8 * buf);
 		}
 	};
 	unsigned rawpar = 0, buf = 0; // rawpar bit b: phase parity of landing buffer b's mbarrier
@@ -252,46 +307,91 @@ __device__ __forceinline__ unsigned run_sorter(unsigned char *ss, uint4 *ebin, u
 	bool inflight = false; // a bulk copy of the CURRENT segment is in flight into raw[buf]
 	if (n && n <= FWD_CAP) { prefetch(s0, n, buf); inflight = true; }
 	unsigned sorted_to = n ? s0 : ntotal;
-	while (n) {
+	bool stopped = false;
+	// m <= FWD_CAP entries at `from` (global) -> sorted into sbin + pos (and the ring slot); raw[buf] is free here
+	auto sort_region = [&](const uint4 *from, unsigned pos, int m) {
+		uint2 *so = acquire_slot();
+		uint4 *rb = raw + buf * FWD_CAP;
+		for (int i = lane; i < m; i += 32) rb[i] = from[i];
+		__syncwarp();
+		warp_sort_segment<SLOT>(sbin + pos, rb, m, so, bkey, bval, hist, lane);
+		__syncwarp();
+		publish(pos, m);
+		sorted_to = pos + (unsigned)m;
+	};
+	while (n && !stopped) {
 		if (!keep_going(sorted_to)) break; // nothing behind this point is read, sorted or gathered
 		next_segment(sloc, k2, k2n, s0n, nn);
-		uint4 *seg = ebin + s0;
 		const bool oversized = n > FWD_CAP;
-		if (oversized) warp_bitonic_sort_global(seg, (int)n, lane);
-		else {
+		if (!oversized) {
 			lgs_mbar_wait(bar_raw + 8 * buf, (rawpar >> buf) & 1u); // the segment has landed in raw[buf]
 			rawpar ^= 1u << buf;
 			inflight = false;
 		}
 		bool inflight_next = false;
 		if (nn && nn <= FWD_CAP) { prefetch(s0n, nn, buf ^ 1u); inflight_next = true; } // overlaps the sort below
-		for (unsigned c0 = 0; c0 < n; c0 += FWD_CAP) {
-			const int m = (int)min((unsigned)FWD_CAP, n - c0);
+		if (!oversized) {
 			uint2 *so = acquire_slot();
-			if (oversized) {
-				if (SLOT) {
-					for (int i = lane; i < m; i += 32) {
-						const uint4 e = seg[c0 + i];
-						so[i] = make_uint2(e.y, e.z);
+			warp_sort_segment<SLOT>(sbin + s0, raw + buf * FWD_CAP, (int)n, so, bkey, bval, hist, lane);
+			publish(s0, (int)n);
+			sorted_to = s0 + n;
+		} else {
+			// ---- one depth bucket with n > FWD_CAP entries ----
+			warp_partition_by_key(ubin + s0, sbin + s0, (int)n, ph1, hist, lane); // sbin: grouped by sub-range
+			int g1 = 0;
+			while (g1 < FWD_NSUB && !stopped) {
+				int g1e;
+				unsigned o1, m1;
+				next_segment(ph1, g1, g1e, o1, m1, FWD_NSUB);
+				if (m1 == 0) break;
+				if (LAZY_INSIDE && !keep_going(sorted_to)) { stopped = true; break; }
+				if (m1 <= FWD_CAP) sort_region(sbin + s0 + o1, s0 + o1, (int)m1);
+				else {
+					// a single sub-range that is still too large: second level, back into the (now free) unsorted positions
+					warp_partition_by_key(sbin + s0 + o1, ubin + s0 + o1, (int)m1, ph2, hist, lane);
+					int g2 = 0;
+					while (g2 < FWD_NSUB && !stopped) {
+						int g2e;
+						unsigned o2, m2;
+						next_segment(ph2, g2, g2e, o2, m2, FWD_NSUB);
+						if (m2 == 0) break;
+						if (LAZY_INSIDE && !keep_going(sorted_to)) { stopped = true; break; }
+						const unsigned pos = s0 + o1 + o2;
+						if (m2 <= FWD_CAP) sort_region(ubin + pos, pos, (int)m2);
+						else { // keys that two levels of 256 linear sub-ranges do not separate: slow, correct
+							for (unsigned i = lane; i < m2; i += 32) sbin[pos + i] = ubin[pos + i];
+							__syncwarp();
+							warp_bitonic_sort_global(sbin + pos, (int)m2, lane);
+							for (unsigned c0 = 0; c0 < m2; c0 += FWD_CAP) {
+								const int m = (int)min((unsigned)FWD_CAP, m2 - c0);
+								uint2 *so = acquire_slot();
+								if (SLOT) {
+									for (int i = lane; i < m; i += 32) {
+										const uint4 e = sbin[pos + c0 + i];
+										so[i] = make_uint2(e.y, e.z);
+									}
+								}
+								publish(pos + c0, m);
+								sorted_to = pos + c0 + (unsigned)m;
+							}
+						}
+						g2 = g2e;
 					}
 				}
-			} else {
-				warp_sort_segment<SLOT>(seg, raw + buf * FWD_CAP, m, so, bkey, bval, hist, lane);
+				g1 = g1e;
 			}
-			publish(s0 + c0, m);
 		}
-		sorted_to = nn ? s0n : ntotal;
 		k2 = k2n; s0 = s0n; n = nn;
 		buf ^= 1u;
 		inflight = inflight_next;
 	}
 	if (inflight) lgs_mbar_wait(bar_raw + 8 * buf, (rawpar >> buf) & 1u); // never leave with a bulk copy in flight
-	return sorted_to;
+	return (n || stopped) ? sorted_to : ntotal;
 }
 
 // ---- kernel A: sort the prefix of every bin ----------------------------------------------------------------------
 __global__ void __launch_bounds__(FWD_GW * 32)
-sort_prefix_kernel(int nbins, const uint32_t *__restrict__ loc, const uint32_t *__restrict__ binbase, uint4 *entries,
+sort_prefix_kernel(int nbins, const uint32_t *__restrict__ loc, const uint32_t *__restrict__ binbase, uint4 *entries, uint4 *unsorted,
 		   uint32_t *__restrict__ sorted_end, uint32_t *__restrict__ alive, const FrameTotals *__restrict__ totals)
 {
 	if (totals->overflow) return; // binning buffer too small for this frame: the host re-runs it (lgs_abi.cu)
@@ -310,8 +410,8 @@ sort_prefix_kernel(int nbins, const uint32_t *__restrict__ loc, const uint32_t *
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncwarp();
-	const unsigned se = run_sorter<false>(
-		ss, entries + base, ntotal, 0, lane, [&](unsigned sorted_to) { return sorted_to < FWD_PREFIX; },
+	const unsigned se = run_sorter<false, false>( // (never stops inside an oversized bucket: kernel C resumes at a bucket boundary)
+		ss, unsorted + base, entries + base, ntotal, 0, lane, [&](unsigned sorted_to) { return sorted_to < FWD_PREFIX; },
 		[&]() { return (uint2 *)nullptr; }, [&](unsigned, int) {});
 	if (lane == 0) {
 		sorted_end[bin] = se;
@@ -548,7 +648,7 @@ render_fwd_groups_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 template <int RB, int ROWS>
 __global__ void __launch_bounds__(TailCfg<RB, ROWS>::NT, TailCfg<RB, ROWS>::NT <= 160 ? 4 : (TailCfg<RB, ROWS>::NT <= 288 ? 2 : 1))
 render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ loc,
-		       const uint32_t *__restrict__ binbase, uint4 *entries, const float *__restrict__ bg,
+		       const uint32_t *__restrict__ binbase, uint4 *entries, uint4 *unsorted, const float *__restrict__ bg,
 		       const float *__restrict__ beams, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
 		       uint32_t *__restrict__ sorted_end, const uint32_t *__restrict__ alive, float4 *__restrict__ fin,
 		       uint4 *__restrict__ cta_prof, float *__restrict__ out_color, float *__restrict__ out_depth,
@@ -596,8 +696,8 @@ render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 		int k0 = 0;
 		while (k0 < LGS_NB && sloc[k0] < se0) k0++; // kernel A sorted whole segments: the prefix ends at a bucket boundary
 		unsigned it = 0;
-		const unsigned se = run_sorter<true>(
-			ss, entries + base, ntotal, k0, lane,
+		const unsigned se = run_sorter<true, true>(
+			ss, unsorted + base, entries + base, ntotal, k0, lane,
 			[&](unsigned) { return sort_all || vdone[0] < (unsigned)NPG; },
 			[&]() {
 				const unsigned slot = it % FWD_NSLOT, par = (it / FWD_NSLOT) & 1u;
@@ -698,7 +798,7 @@ template <int RB> struct PipeCfg {
 template <int RB>
 __global__ void __launch_bounds__(PipeCfg<RB>::NT, PipeCfg<RB>::NT <= 288 ? 2 : 1)
 render_fwd_pipe_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ loc,
-		       const uint32_t *__restrict__ binbase, uint4 *entries, const float *__restrict__ bg,
+		       const uint32_t *__restrict__ binbase, uint4 *entries, uint4 *unsorted, const float *__restrict__ bg,
 		       const float *__restrict__ beams, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
 		       uint32_t *__restrict__ sorted_end, float4 *__restrict__ fin, uint4 *__restrict__ cta_prof,
 		       float *__restrict__ out_color, float *__restrict__ out_depth, float *__restrict__ out_occ, int sort_all,
@@ -760,8 +860,8 @@ render_fwd_pipe_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 		// =============================== sorter warp (as in kernel C) ===============================
 		const volatile unsigned *vdone = sctl;
 		unsigned it = 0;
-		const unsigned se = run_sorter<true>(
-			ss, entries + base, ntotal, 0, lane, [&](unsigned) { return sort_all || vdone[0] < (unsigned)NPG; },
+		const unsigned se = run_sorter<true, true>(
+			ss, unsorted + base, entries + base, ntotal, 0, lane, [&](unsigned) { return sort_all || vdone[0] < (unsigned)NPG; },
 			[&]() {
 				const unsigned slot = it % FWD_NSLOT, par = (it / FWD_NSLOT) & 1u;
 				lgs_mbar_wait(bar_empty + 8 * slot, par ^ 1u);
@@ -986,7 +1086,7 @@ render_fwd_pipe_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 }
 
 template <int RB>
-void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries, const float *bg,
+void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries, uint4 *unsorted, const float *bg,
 		const float *beams, float *out_color, float *out_depth, float *out_occ, int sort_all, int split, unsigned *walk_stat,
 		cudaStream_t st)
 {
@@ -995,7 +1095,7 @@ void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uin
 	if (split == 2) { // evaluate / blend on separate warps
 		using CP = PipeCfg<RB>;
 		cudaFuncSetAttribute(render_fwd_pipe_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CP::BYTES);
-		render_fwd_pipe_kernel<RB><<<g.nbins, CP::NT, CP::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, bg, beams, ip.final_T,
+		render_fwd_pipe_kernel<RB><<<g.nbins, CP::NT, CP::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, unsorted, bg, beams, ip.final_T,
 									       ip.n_contrib, ip.sorted_end, ip.fin, ip.cta_prof, out_color, out_depth,
 									       out_occ, sort_all, gp.order, gp.totals, walk_stat);
 		return;
@@ -1003,7 +1103,7 @@ void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uin
 	if (split == 3) { // one worker warp per pixel ROW (twice the warps per bin: shorter critical path, half-empty blend)
 		using C1 = TailCfg<RB, 1>;
 		cudaFuncSetAttribute(render_fwd_tail_kernel<RB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1::BYTES);
-		render_fwd_tail_kernel<RB, 1><<<g.nbins, C1::NT, C1::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, bg, beams, ip.final_T,
+		render_fwd_tail_kernel<RB, 1><<<g.nbins, C1::NT, C1::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, unsorted, bg, beams, ip.final_T,
 										  ip.n_contrib, ip.sorted_end, ip.alive, ip.fin, ip.cta_prof, out_color,
 										  out_depth, out_occ, sort_all, 1, gp.order, gp.totals, walk_stat);
 		return;
@@ -1012,28 +1112,28 @@ void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uin
 	if (split) {
 		const size_t smA = FWD_GW * SortSmem::BYTES, smB = FWD_GW * WorkSmem::BYTES;
 		cudaFuncSetAttribute(sort_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smA);
-		sort_prefix_kernel<<<(g.nbins + FWD_GW - 1) / FWD_GW, FWD_GW * 32, smA, st>>>(g.nbins, gp.loc, gp.binbase, entries,
+		sort_prefix_kernel<<<(g.nbins + FWD_GW - 1) / FWD_GW, FWD_GW * 32, smA, st>>>(g.nbins, gp.loc, gp.binbase, entries, unsorted,
 											     ip.sorted_end, ip.alive, gp.totals);
 		render_fwd_groups_kernel<RB><<<(g.nbins * NPG + FWD_GW - 1) / FWD_GW, FWD_GW * 32, smB, st>>>(
 			g, gp.rec, gp.binbase, entries, bg, beams, ip.final_T, ip.n_contrib, ip.sorted_end, ip.alive, ip.fin, out_color,
 			out_depth, out_occ, gp.totals);
 	}
-	render_fwd_tail_kernel<RB, 2><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, bg, beams, ip.final_T,
+	render_fwd_tail_kernel<RB, 2><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, unsorted, bg, beams, ip.final_T,
 								     ip.n_contrib, ip.sorted_end, ip.alive, ip.fin, ip.cta_prof, out_color,
 								     out_depth, out_occ, sort_all, split ? 0 : 1, gp.order, gp.totals, walk_stat);
 }
 
 } // namespace
 
-void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries,
+void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries, uint4 *unsorted,
 			   const float *bg, const float *beams, float *out_color, float *out_depth, float *out_occ,
 			   int sort_all, int split, unsigned *walk_stat, cudaStream_t st)
 {
 	switch (g.RB) {
-	case 1: launch_fwd<1>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
-	case 2: launch_fwd<2>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
-	case 4: launch_fwd<4>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
-	case 8: launch_fwd<8>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
-	default: launch_fwd<16>(g, gp, ip, entries, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
+	case 1: launch_fwd<1>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
+	case 2: launch_fwd<2>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
+	case 4: launch_fwd<4>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
+	case 8: launch_fwd<8>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
+	default: launch_fwd<16>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
 	}
 }
