@@ -10,7 +10,7 @@ import json
 d=json.loads(open('gpurun_out/${TAG}_bench.json').read())
 print('frames/s', round(d['value'],1), 'ms/step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value'],1), 'launches', d['gpu_launches'])
 print({k:round(v['ms_per_step'],3) for k,v in d['extra']['stages'].items()})
-print('roofline', d['roofline']['kernel'], round(d['roofline']['frac'],4), 'bubble', d['extra']['host_bubble_ms'], 'step_ms', d['extra']['step_ms'])
+print('roofline', d['roofline']['kernel'], round(d['roofline']['frac'],4), 'step_ms', d['extra']['step_ms'], 'mode', d['extra']['forward_mode'])
 print('cpu', d['cpu_baseline'])
 for k,v in d['extra'].get('workloads',{}).items():
     print(k, {kk:(round(vv['ms_median'],3) if isinstance(vv,dict) and 'ms_median' in vv else vv) for kk,vv in v.items()})
