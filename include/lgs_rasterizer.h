@@ -377,7 +377,7 @@ long long lgs_last_num_instances(void);
 /*
  * The binning buffer (the reference sizes it after a blocking read-back of num_rendered, rasterizer_impl.cu:292-296)
  * is requested from the callback BEFORE the instance count of the frame is known, sized from the previous frame of
- * the same shape + 25 % (first frame: 4 P), as 36 bytes per instance (20 on the surfel path); a frame that does not fit is detected on the
+ * the same shape + 25 % (first frame: 4 P), as 36 bytes per instance; a frame that does not fit is detected on the
  * device and re-run once with the exact size (a second call of the binning callback).
  * lgs_overflow_reruns(): how many frames of this thread were re-run.  lgs_set_capacity_hint(n > 0) forces the first
  * guess of every following frame to n instances (tests); 0 restores the automatic sizing.

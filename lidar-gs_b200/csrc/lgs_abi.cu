@@ -166,14 +166,13 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 	else cap = 4 * (size_t)g.P + 4096;
 	for (int attempt = 0;; attempt++) {
 		if (cap > 0xfffffff0ull) return fail(LGS_EINVAL, "binning buffer would exceed 2^32 instances");
-		// 3-D path: sorted lists (offset 0: what the backward pass is handed) | lists as scattered | rank stream = 36 B per
-		// instance; surfel path (sorts in place): lists | rank stream = 20 B per instance
+		// sorted lists (offset 0: what the backward pass is handed) | lists as scattered | rank stream = 36 B per instance
 		const size_t list_bytes = lgs_al(cap * sizeof(uint4));
-		const size_t ranks_off = (path == 0 ? 2 : 1) * list_bytes;
+		const size_t ranks_off = 2 * list_bytes;
 		char *bb = binning_buffer(ranks_off + cap * sizeof(uint32_t), binning_user);
 		if (!bb) return fail(LGS_ENOMEM, "binning callback returned NULL");
 		uint4 *entries = (uint4 *)bb;
-		uint4 *scattered = path == 0 ? (uint4 *)(bb + list_bytes) : entries;
+		uint4 *scattered = (uint4 *)(bb + list_bytes);
 		uint32_t *ranks = (uint32_t *)(bb + ranks_off);
 		g_timer.begin(LGS_STAGE_CLEAR, st);
 		CK(cudaMemsetAsync(gp.cnt, 0, (size_t)g.nbins * LGS_NB * 4, st));
@@ -443,8 +442,8 @@ int lgs_surfel_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_al
 			lgs_launch_surfel_project(g, means3D, scales, scale_modifier, rotations, opacities, colors_precomp, viewmatrix,
 						  beam_inclinations, far, near, gp, radii, radii_xy, ranks, cap, st);
 		},
-		[&](uint4 *entries, uint4 *, DevState *) {
-			lgs_launch_surfel_render_fwd(g, gp, ip, entries, background, beam_inclinations, out_color, out_others,
+		[&](uint4 *entries, uint4 *scattered, DevState *) {
+			lgs_launch_surfel_render_fwd(g, gp, ip, entries, scattered, background, beam_inclinations, out_color, out_others,
 						     g_sort_all.load(), st);
 		},
 		&R);

@@ -47,7 +47,7 @@ void lgs_launch_surfel_filter(int P, const float *means3D, const float *scales, 
 			      const float *view, int W, int H, const float *beams, int far_, int near_, int *radii, int *radii_xy,
 			      cudaStream_t st);
 void lgs_launch_surfel_mark_visible(int P, const float *means3D, const float *view, unsigned char *present, cudaStream_t st);
-void lgs_launch_surfel_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const SurfelImagePtrs &ip, uint4 *entries,
+void lgs_launch_surfel_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const SurfelImagePtrs &ip, uint4 *entries, uint4 *unsorted,
 				  const float *bg, const float *beams, float *out_color, float *out_others, int sort_all,
 				  cudaStream_t st);
 void lgs_launch_surfel_render_bwd(const FrameGeom &g, const GeomPtrs &gp, const SurfelImagePtrs &ip, const uint4 *entries,

@@ -21,7 +21,7 @@ LIB = os.path.join(LIBDIR, "liblgs_b200.so")
 EXT = os.path.join(PKG, "diff_lidargs_rasterization", "_C.so")
 CU = ["lgs_project.cu", "lgs_bin.cu", "lgs_render_fwd.cu", "lgs_render_bwd.cu", "lgs_finalize_bwd.cu", "lgs_abi.cu",
       "lgs_surfel_project.cu", "lgs_surfel_render.cu", "lgs_dp.cu", "lgs_decode.cu", "lgs_loss.cu", "lgs_eval.cu", "lgs_adam.cu"]
-HDRS = ["lgs_common.cuh", "lgs_kernels.h", "lgs_sort.cuh", "lgs_surfel.cuh", os.path.join(ROOT, "include", "lgs_rasterizer.h")]
+HDRS = ["lgs_common.cuh", "lgs_kernels.h", "lgs_sorter.cuh", "lgs_surfel.cuh", os.path.join(ROOT, "include", "lgs_rasterizer.h")]
 NVCC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

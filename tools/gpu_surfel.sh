@@ -1,9 +1,15 @@
 #!/bin/bash
-# GPU box: surfel parity tests, smoke, then the config-5 bench line (+ reference arm).  gpurun --timeout 1500 -- bash tools/gpu_surfel.sh [tag]
-TAG=${1:-r01s}
+# GPU box (1 GPU): the surfel test file, then the cfg5 bench line.      usage: gpu_surfel.sh <tag> [skip-tests]
+TAG=${1:-surfel}
 mkdir -p gpurun_out
-echo "== pytest surfel"; timeout 1200 python -m pytest tests/test_gpu_surfel.py -q -m gpu --tb=short -p no:cacheprovider -x 2>&1 | tail -30 | tee gpurun_out/${TAG}_pytest_surfel.txt
-echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4 | tee gpurun_out/${TAG}_smoke.txt
-echo "== bench surfel"; timeout 600 python bench.py --workload surfel 2>gpurun_out/${TAG}_bench_surfel.err | tee gpurun_out/${TAG}_bench_surfel.json
+if [ -z "$2" ]; then
+timeout 900 python -m pytest tests/test_gpu_surfel.py -q --tb=short -p no:cacheprovider -x 2>&1 | tail -25
+fi
+timeout 600 python bench.py --workload surfel --no-cpu --no-e2e --no-workloads 2>gpurun_out/${TAG}_bench_surfel.err | tail -1 > gpurun_out/${TAG}_bench_surfel.json
 tail -3 gpurun_out/${TAG}_bench_surfel.err
-echo "== bench surfel reference arm"; timeout 600 python bench.py --workload surfel --impl reference --steps 2 --warmup 1 2>&1 | tail -2 | tee gpurun_out/${TAG}_bench_surfel_ref.json
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/${TAG}_bench_surfel.json').read())
+print('frames/s', round(d['value'],1), 'ms/step', round(d['ms_per_step'],4))
+print({k:round(v['ms_per_step'],3) for k,v in d['extra']['stages'].items()})
+PY
