@@ -262,6 +262,8 @@ def run_surfel(args, rank, world, local):
         dist.init_process_group("nccl", device_id=dev)
     L = capi.load()
     L.lgs_set_rows_per_bin(args.rows_per_bin)
+    if args.forward_mode is not None:
+        L.lgs_set_forward_split(args.forward_mode)
     sc["viewmatrix"] = rank_pose(sc, rank if args.pose_rank is None else args.pose_rank)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     d = {k: t(v) for k, v in sc.items() if isinstance(v, np.ndarray)}

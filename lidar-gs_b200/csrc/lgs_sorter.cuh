@@ -9,7 +9,9 @@
 
 namespace {
 
-#define FWD_CAP 512      // entries per segment (a single depth bucket larger than this is "oversized")
+#ifndef FWD_CAP
+#define FWD_CAP 512      // entries per segment (a single depth bucket larger than this is "oversized"); a multiple of 32
+#endif
 #define FWD_TARGET 128   // buckets are grouped until a segment has at least this many entries
 #define FWD_NSUB 256     // sub-buckets of the counting sort
 #define FWD_NSLOT 2      // kernel C's ring depth: how far the sorter may run ahead of the slowest worker

@@ -20,12 +20,14 @@
 //              five 16-byte vector reductions into the packed [P, 20] accumulator (the reference: ~30 scalar atomics
 //              per pair).
 #include "lgs_surfel.cuh"
+#define FWD_CAP 256 // smaller sorter segments than the 3-D path: 4 CTAs per SM (the 80-B records make the workers register-heavy)
 #include "lgs_sorter.cuh"
 #include "lgs_kernels.h"
 
 namespace {
 
-#define SF_NCOL 2 // columns evaluated per trip by every lane of the forward evaluate phase (independent dependency chains)
+#define SF_NCOL 2 // columns evaluated per trip by every lane of the forward evaluate phase (independent dependency chains;
+                  // 4 measured no faster, 1 slower)
 
 // shared memory of one forward worker warp (bytes)
 struct SWorkSmem {
@@ -36,7 +38,8 @@ struct SWorkSmem {
 	static constexpr size_t RAY = PFB + 8 * 32;                // float4 per pixel, index column * 2 + row
 	static constexpr size_t PMASK = RAY + 16 * 32;             // u32 per pixel (index row * 16 + column)
 	static constexpr size_t QUEUE = PMASK + 4 * 32;            // uint2 (id, list position << 1 | row) ring
-	static constexpr size_t BYTES = QUEUE + 8 * FWD_QCAP;
+	static constexpr size_t STATE = QUEUE + 8 * FWD_QCAP;      // float [13][32]: the per-pixel accumulators between two blends
+	static constexpr size_t BYTES = STATE + 4 * 13 * 32;
 };
 template <int RB> struct SFwdCfg {
 	static constexpr int NPG = RB >= 2 ? RB / 2 : 1; // worker warps
@@ -55,6 +58,7 @@ template <int RB> struct SFwdCfg {
 struct SurfelWorker {
 	// shared memory of this warp
 	float *ta, *td; float4 *pfa; float2 *pfb; float4 *sray; unsigned *pmask; uint2 *queue;
+	float *sst; // this lane's column of the state planes
 	// identity
 	int lane, hrow, pcol, rowbase, row0, px, py;
 	float pxbase;
@@ -62,9 +66,9 @@ struct SurfelWorker {
 	bool inside;
 	const float4 *rec;
 	uint4 *ebin; // the bin's sorted list
-	// pixel state (lanes = pixels: row rowbase + lane / 16, column lane % 16), fwd.cu:400-420
-	float T, C0, C1, D, M1, M2, dist, Nx, Ny, Nz, med_depth;
-	unsigned last, medpos; // 1-based list positions of the last blended entry / of the median-depth entry
+	// pixel state (lanes = pixels: row rowbase + lane / 16, column lane % 16), fwd.cu:400-420: T, C0, C1, D, M1, M2,
+	// distortion, N.xyz, median depth, last (1-based list position of the last blended entry), medpos (... of the median-
+	// depth entry) live in shared memory between two blends: the evaluate phase then has the registers for its pair chains
 	bool done;
 	unsigned live; // bit (row * 16 + column)
 	// pair queue (uniform) and the pending chunk: pairs whose records are in flight / in registers
@@ -91,8 +95,10 @@ struct SurfelWorker {
 		inside = px < g.W && py < g.H && rowbase + hrow < RB;
 		row0 = rg * RB + rowbase;
 		lt = (1u << lane) - 1u;
-		T = 1.0f; C0 = C1 = D = M1 = M2 = dist = Nx = Ny = Nz = med_depth = 0.f;
-		last = 0; medpos = 0;
+		sst = reinterpret_cast<float *>(wb + SWorkSmem::STATE) + lane;
+		sst[0] = 1.0f; // T
+#pragma unroll
+		for (int i = 1; i < 13; i++) sst[32 * i] = 0.f;
 		PixelRay ray = {0.f, 0.f, 0.f};
 		if (inside) ray = lgs_pixel_ray(px, py, g.W, g.H, beams); // fwd.cu:435-446 (same expression as the 3-D path)
 		sray[pcol * 2 + hrow] = make_float4(ray.x, ray.y, ray.z, 0.f);
@@ -160,8 +166,11 @@ struct SurfelWorker {
 		__syncwarp();
 		// ---- blend: every lane walks the pairs that touch ITS pixel, in list order (fwd.cu:487-522) ----
 		unsigned blended = 0;
-		if (!done) {
-			unsigned mk = ((hrow ? rs1 : rs0) != 0u) ? pmask[lane] : 0u; // (a row without pairs was not visited: stale mask)
+		unsigned mk = (!done && (hrow ? rs1 : rs0) != 0u) ? pmask[lane] : 0u; // (a row without pairs was not visited: stale mask)
+		if (mk) {
+			float T = sst[0], C0 = sst[32], C1 = sst[64], D = sst[96], M1 = sst[128], M2 = sst[160], dist = sst[192], Nx = sst[224],
+			      Ny = sst[256], Nz = sst[288], med_depth = sst[320];
+			unsigned last = __float_as_uint(sst[352]), medpos = __float_as_uint(sst[384]);
 			const float *tra = ta + (size_t)pcol * FWD_TLD, *trd = td + (size_t)pcol * FWD_TLD;
 			while (mk) {
 				const int i = __ffs(mk) - 1;
@@ -188,6 +197,9 @@ struct SurfelWorker {
 				last = p1;
 				blended |= 1u << i;
 			}
+			sst[0] = T; sst[32] = C0; sst[64] = C1; sst[96] = D; sst[128] = M1; sst[160] = M2; sst[192] = dist; sst[224] = Nx;
+			sst[256] = Ny; sst[288] = Nz; sst[320] = med_depth;
+			sst[352] = __uint_as_float(last); sst[384] = __uint_as_float(medpos);
 		}
 		// the backward pass only revisits (entry, row) pairs that blended: flags ride in the entry's spare word
 		const unsigned bl = __reduce_or_sync(0xffffffffu, blended);
@@ -236,6 +248,9 @@ struct SurfelWorker {
 					      float *__restrict__ out_color, float *__restrict__ out_others) const
 	{
 		if (!inside) return;
+		const float T = sst[0], C0 = sst[32], C1 = sst[64], D = sst[96], M1 = sst[128], dist = sst[192], Nx = sst[224], Ny = sst[256],
+			    Nz = sst[288], med_depth = sst[320];
+		const unsigned last = __float_as_uint(sst[352]), medpos = __float_as_uint(sst[384]);
 		const size_t pix = (size_t)py * g.W + px, HW = (size_t)g.H * g.W;
 		ip.final_T[pix] = T;
 		ip.n_contrib[pix] = last;
@@ -253,8 +268,9 @@ struct SurfelWorker {
 	}
 };
 
+// 4 CTAs per SM (<= 102 registers, 52 KB of shared memory): 1.52 ms on cfg5 against 1.75 ms with 3
 template <int RB>
-__global__ void __launch_bounds__(SFwdCfg<RB>::NT, 3)
+__global__ void __launch_bounds__(SFwdCfg<RB>::NT, 4)
 surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ loc,
 			 const uint32_t *__restrict__ binbase, const uint32_t *__restrict__ order, uint4 *entries, uint4 *unsorted,
 			 const float *__restrict__ bg, const float *__restrict__ beams, SurfelImagePtrs ip, float *__restrict__ out_color,
