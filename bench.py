@@ -264,6 +264,8 @@ def run_surfel(args, rank, world, local):
     L.lgs_set_rows_per_bin(args.rows_per_bin)
     if args.forward_mode is not None:
         L.lgs_set_forward_split(args.forward_mode)
+    if args.no_order_history:
+        L.lgs_set_order_history(0)
     sc["viewmatrix"] = rank_pose(sc, rank if args.pose_rank is None else args.pose_rank)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     d = {k: t(v) for k, v in sc.items() if isinstance(v, np.ndarray)}
@@ -530,6 +532,7 @@ def main():
                          "step k overlaps filter + forward of step k + 1 and is waited for before that step's backward rewrites the bucket)")
     ap.add_argument("--no-workloads", action="store_true", help="skip extra.workloads (other configs / poses, each vs the reference CUDA)")
     ap.add_argument("--forward-mode", type=int, default=None, help="lgs_set_forward_split(mode): 0 one pipelined kernel, 1 split, 2 evaluate/blend warps")
+    ap.add_argument("--no-order-history", action="store_true", help="lgs_set_order_history(0): launch order from list lengths only")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-dense-grads", action="store_true",
                     help="end-to-end leg copies the dense gradient arrays to the host instead of the non-zero rows")
@@ -561,6 +564,8 @@ def main():
     L.lgs_set_rows_per_bin(args.rows_per_bin)
     if args.forward_mode is not None:
         L.lgs_set_forward_split(args.forward_mode)
+    if args.no_order_history:
+        L.lgs_set_order_history(0)
 
     sc = synth.make_config(CFG)
     sc["viewmatrix"] = rank_pose(sc, rank if args.pose_rank is None else args.pose_rank)

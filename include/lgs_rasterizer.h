@@ -367,6 +367,11 @@ int lgs_set_sort_all(int on);
  *    2 one launch, evaluate and blend on separate warps coupled by an mbarrier ring
  */
 int lgs_set_forward_split(int mode);
+/* 1 (default): the compositing pass launches its bins in the order of how far each bin's list was walked in the previous
+ * frame of the same geometry on this device (deepest first: the scene and the sensor change little from one frame of a
+ * sequence to the next); 0: order by list length only (what the first frame always uses).  A scheduling hint: the images
+ * do not depend on it. */
+int lgs_set_order_history(int on);
 /* The shape (0 .. 3) the last lgs_forward() of this thread actually used. */
 int lgs_last_forward_mode(void);
 /* Longest walk (chunks of 32 (entry, row) pairs, in two-row-worker units) of any pixel group in the frame BEFORE the last

@@ -32,12 +32,15 @@ struct DevState {
 	struct Hwm { int P = -1, W = 0, H = 0; long long N = 0; } hwm[2]; // [0] 3-D path, [1] surfel path
 	unsigned *walk_stat = nullptr; // device word: longest walk of the last compositing pass (see FrameTotals::prev_max_chunks)
 	int one_row_workers = 0;       // worker shape the automatic mode currently uses on this device
+	// how far every bin's list was walked in the last frame of this geometry: the launch order of the next one (lgs_bin.cu)
+	struct Cost { uint32_t *dev = nullptr; int nbins = 0, W = 0, H = 0, RB = 0; bool valid = false; } cost[2];
 };
 #define LGS_MAX_DEVICES 64
 thread_local DevState g_dev[LGS_MAX_DEVICES];
 std::atomic<int> g_rows_per_bin{0};
 std::atomic<int> g_sort_all{0};
 std::atomic<int> g_fwd_split{-1}; // -1: automatic worker shape (see bin_and_render)
+std::atomic<int> g_order_history{1}; // launch order of the compositing pass from the previous frame's walk depths
 std::atomic<long long> g_launches{0};
 std::atomic<long long> g_capacity_hint{0}; // test knob: forces the capacity guess of the next frames (0 = automatic)
 
@@ -164,6 +167,16 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 	if (g_capacity_hint.load() > 0) cap = (size_t)g_capacity_hint.load();
 	else if (hw.P == g.P && hw.W == g.W && hw.H == g.H && hw.N > 0) cap = (size_t)hw.N + (size_t)hw.N / 4 + 4096;
 	else cap = 4 * (size_t)g.P + 4096;
+	// launch-order hint: per-bin walk depth of the previous frame of the same geometry on this device
+	DevState::Cost &co = ds->cost[path];
+	if (co.nbins != g.nbins || co.W != g.W || co.H != g.H || co.RB != g.RB) {
+		if (co.dev) cudaFree(co.dev);
+		co = DevState::Cost();
+		CK(cudaMalloc(&co.dev, (size_t)g.nbins * sizeof(uint32_t)));
+		CK(cudaMemsetAsync(co.dev, 0, (size_t)g.nbins * sizeof(uint32_t), st));
+		co.nbins = g.nbins; co.W = g.W; co.H = g.H; co.RB = g.RB;
+	}
+	const bool use_history = g_order_history.load() != 0;
 	for (int attempt = 0;; attempt++) {
 		if (cap > 0xfffffff0ull) return fail(LGS_EINVAL, "binning buffer would exceed 2^32 instances");
 		// sorted lists (offset 0: what the backward pass is handed) | lists as scattered | rank stream = 36 B per instance
@@ -182,7 +195,8 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 		project(ranks, (unsigned)cap);
 		g_timer.end(st);
 		g_timer.begin(LGS_STAGE_SCAN, st);
-		lgs_launch_scan(g, gp, ds->pinned_dev, (unsigned)cap, path == 0 ? ds->walk_stat : nullptr, st);
+		lgs_launch_scan(g, gp, ds->pinned_dev, (unsigned)cap, path == 0 ? ds->walk_stat : nullptr,
+				use_history && co.valid ? co.dev : nullptr, st);
 		g_timer.end(st);
 		CK(cudaEventRecord(ds->scan_done, st));
 		g_timer.begin(LGS_STAGE_SCATTER, st);
@@ -211,6 +225,7 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 		if (N <= cap) {
 			hw.P = g.P; hw.W = g.W; hw.H = g.H;
 			hw.N = (long long)N;
+			co.valid = true; // (the compositing pass of this frame is writing it)
 			return 0;
 		}
 		if (attempt >= 1) return fail(LGS_ECUDA, "binning buffer overflow after re-sizing (internal error)");
@@ -277,7 +292,7 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn 
 			if (mode < 0) mode = ds->one_row_workers ? 3 : 0;
 			g_last_fwd_mode = mode;
 			lgs_launch_render_fwd(g, gp, ip, entries, scattered, background, beam_inclinations, out_color, out_depth, out_occ,
-					      g_sort_all.load(), mode, ds->walk_stat, st);
+					      g_sort_all.load(), mode, ds->walk_stat, ds->cost[0].dev, st);
 		},
 		&R);
 	if (rc < 0) return rc;
@@ -442,9 +457,9 @@ int lgs_surfel_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_al
 			lgs_launch_surfel_project(g, means3D, scales, scale_modifier, rotations, opacities, colors_precomp, viewmatrix,
 						  beam_inclinations, far, near, gp, radii, radii_xy, ranks, cap, st);
 		},
-		[&](uint4 *entries, uint4 *scattered, DevState *) {
+		[&](uint4 *entries, uint4 *scattered, DevState *ds) {
 			lgs_launch_surfel_render_fwd(g, gp, ip, entries, scattered, background, beam_inclinations, out_color, out_others,
-						     g_sort_all.load(), st);
+						     g_sort_all.load(), ds->cost[1].dev, st);
 		},
 		&R);
 	if (rc < 0) return rc;
@@ -546,6 +561,11 @@ int lgs_set_forward_split(int mode)
 {
 	if (mode < -1 || mode > 3) return fail(LGS_EINVAL, "lgs_set_forward_split: mode must be -1 .. 3");
 	g_fwd_split.store(mode);
+	return 0;
+}
+int lgs_set_order_history(int on)
+{
+	g_order_history.store(on != 0);
 	return 0;
 }
 int lgs_timing_enable(int on)

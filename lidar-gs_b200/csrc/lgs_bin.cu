@@ -45,7 +45,8 @@ scan_bins_kernel(int nbins, uint32_t *__restrict__ cnt, uint32_t *__restrict__ l
 // single block: exclusive scan of the per-bin totals (in place: binbase[b] holds total on entry)
 __global__ void __launch_bounds__(1024)
 scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__restrict__ totals, uint32_t *__restrict__ order,
-		  FrameTotals *__restrict__ host_totals, unsigned capacity, unsigned *__restrict__ walk_stat)
+		  FrameTotals *__restrict__ host_totals, unsigned capacity, unsigned *__restrict__ walk_stat,
+		  const uint32_t *__restrict__ prev_cost)
 {
 	__shared__ unsigned wsum[32];
 	__shared__ unsigned carry_s;
@@ -88,34 +89,35 @@ scan_total_kernel(int nbins, uint32_t *__restrict__ binbase, FrameTotals *__rest
 			__threadfence_system();
 		}
 	}
-	// Launch order of the render kernels: bins by ASCENDING list length (64 linear classes).  A dense bin saturates
-	// after a few hundred entries whatever its length; the expensive bins are the sparse ones, whose rays never
-	// terminate and walk their whole list -- so short lists go first and the tail of the grid is made of the uniform,
-	// cheap, dense bins.
+	// Launch order of the render kernels (32 linear classes of a per-bin cost estimate, most expensive first: the expensive
+	// bins are the ones whose rays never terminate and walk their whole list, and a bin that starts late ends late).
+	//   with history  : cost = how far the bin's list was walked (sorted) in the previous frame of this geometry on this
+	//                   device -- the scene and the sensor change little from one frame of a sequence to the next;
+	//   without       : shortest list first.  A dense bin saturates after a few hundred entries whatever its length; the
+	//                   sparse ones walk everything, so the tail of the grid is made of the uniform, cheap, dense bins.
 	__shared__ unsigned smaxt;
 	if (threadIdx.x == 0) smaxt = 0;
 	__syncthreads();
+	auto keyof = [&](int i) { return prev_cost ? prev_cost[i] : binbase[i + 1] - binbase[i]; };
 	unsigned mx = 0;
-	for (int i = threadIdx.x; i < nbins; i += 1024) mx = max(mx, binbase[i + 1] - binbase[i]);
+	for (int i = threadIdx.x; i < nbins; i += 1024) mx = max(mx, keyof(i));
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
 	if (lane == 0) atomicMax(&smaxt, mx);
 	__syncthreads();
 	const unsigned long long maxt = (unsigned long long)smaxt + 1ull;
-	for (int i = threadIdx.x; i < nbins; i += 1024) {
-		unsigned t = binbase[i + 1] - binbase[i];
-		atomicAdd(&hist[(unsigned)((unsigned long long)t * 32ull / maxt)], 1u);
-	}
+	auto classof = [&](int i) {
+		const unsigned c = (unsigned)((unsigned long long)keyof(i) * 32ull / maxt);
+		return prev_cost ? 31u - c : c;
+	};
+	for (int i = threadIdx.x; i < nbins; i += 1024) atomicAdd(&hist[classof(i)], 1u);
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		unsigned run = 0;
 		for (int c = 0; c < 33; c++) { start[c] = run; run += hist[c]; }
 	}
 	__syncthreads();
-	for (int i = threadIdx.x; i < nbins; i += 1024) {
-		unsigned t = binbase[i + 1] - binbase[i];
-		order[atomicAdd(&start[(unsigned)((unsigned long long)t * 32ull / maxt)], 1u)] = (unsigned)i;
-	}
+	for (int i = threadIdx.x; i < nbins; i += 1024) order[atomicAdd(&start[classof(i)], 1u)] = (unsigned)i;
 }
 
 // One thread per Gaussian; a Gaussian with a large footprint (near range: hundreds of bins) is expanded by its
@@ -168,11 +170,11 @@ scatter_kernel(int P, int gx, int RB, int far_, int near_, const uint4 *__restri
 } // namespace
 
 void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, unsigned capacity, unsigned *walk_stat,
-		     cudaStream_t st)
+		     const uint32_t *prev_cost, cudaStream_t st)
 {
 	int warps_per_block = 8;
 	scan_bins_kernel<<<(g.nbins + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(g.nbins, gp.cnt, gp.loc, gp.binbase);
-	scan_total_kernel<<<1, 1024, 0, st>>>(g.nbins, gp.binbase, gp.totals, gp.order, host_totals, capacity, walk_stat);
+	scan_total_kernel<<<1, 1024, 0, st>>>(g.nbins, gp.binbase, gp.totals, gp.order, host_totals, capacity, walk_stat, prev_cost);
 }
 
 void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, const uint32_t *ranks, unsigned capacity,

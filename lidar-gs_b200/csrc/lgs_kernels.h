@@ -16,6 +16,7 @@ void lgs_launch_mark_visible(int P, const float *means3D, const float *view, uns
 
 // bucket counts -> per-bin exclusive offsets (loc), bin bases (binbase), totals->num_instances / overflow; cnt reset to 0
 void lgs_launch_scan(const FrameGeom &g, const GeomPtrs &gp, FrameTotals *host_totals, unsigned capacity, unsigned *walk_stat,
+		     const uint32_t *prev_cost,
 		     cudaStream_t st);
 // (Gaussian, bin) instances -> entries[], bin-major / bucket-minor, unordered inside a bucket; positions from the rank stream
 void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, const uint32_t *ranks, unsigned capacity,
@@ -25,7 +26,7 @@ void lgs_launch_scatter(const FrameGeom &g, const GeomPtrs &gp, uint4 *entries, 
 // unsorted: the lists as the scatter kernel left them (the sorter's input, and its scratch for oversized depth buckets)
 void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries, uint4 *unsorted,
 			   const float *bg, const float *beams, float *out_color, float *out_depth, float *out_occ,
-			   int sort_all, int split, unsigned *walk_stat, cudaStream_t st);
+			   int sort_all, int split, unsigned *walk_stat, uint32_t *bin_cost, cudaStream_t st);
 void lgs_launch_render_bwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, const uint4 *entries,
 			   const float *bg, const float *beams, const float *dL_dpix, const float *dL_ddepth,
 			   const float *dL_docc, float *grad, cudaStream_t st);
@@ -49,7 +50,7 @@ void lgs_launch_surfel_filter(int P, const float *means3D, const float *scales, 
 void lgs_launch_surfel_mark_visible(int P, const float *means3D, const float *view, unsigned char *present, cudaStream_t st);
 void lgs_launch_surfel_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const SurfelImagePtrs &ip, uint4 *entries, uint4 *unsorted,
 				  const float *bg, const float *beams, float *out_color, float *out_others, int sort_all,
-				  cudaStream_t st);
+				  uint32_t *bin_cost, cudaStream_t st);
 void lgs_launch_surfel_render_bwd(const FrameGeom &g, const GeomPtrs &gp, const SurfelImagePtrs &ip, const uint4 *entries,
 				  const float *bg, const float *beams, const float *dL_dpix, const float *dL_dothers, float *grad,
 				  cudaStream_t st);

@@ -34,6 +34,9 @@
 //                  reference's order and arithmetic -- so a lane only ever executes pairs that touch its pixel.
 //                 Evaluate and blend alternate inside the warp (__syncwarp only).
 // Same (pixel, Gaussian) pairs, same arithmetic per pair, same blend order => bit-identical images.
+#ifndef FWD_CAP
+#define FWD_CAP 256 // entries per sorter segment
+#endif
 #include "lgs_sorter.cuh"
 #include "lgs_kernels.h"
 
@@ -56,18 +59,15 @@ template <int RB, int ROWS = 2> struct TailCfg {
 	static constexpr int NPG = RB >= ROWS ? RB / ROWS : 1; // worker warps: one per ROWS rows x 16 columns of the bin
 	static constexpr int NW = NPG + 1;                    // + the sorter warp (last)
 	static constexpr int NT = NW * 32;
-	static constexpr size_t O_BAR = 0;                                   // full[NSLOT], empty[NSLOT] mbarriers
-	static constexpr size_t O_CTL = O_BAR + 8 * 2 * FWD_NSLOT;           // groups done, warps finished, chunks
-	static constexpr size_t O_DESC = O_CTL + 16;                         // uint4 per slot: {list position, count, end, -}
-	static constexpr size_t O_SLOT = O_DESC + 16 * FWD_NSLOT;            // uint2 (id, y0 | y1 << 16) per sorted entry
-	static constexpr size_t O_SORT = O_SLOT + 8 * FWD_CAP * FWD_NSLOT;   // SortSmem
+	static constexpr size_t O_FEED = 0;                                  // SortFeed
+	static constexpr size_t O_SORT = (sizeof(SortFeed) + 15) / 16 * 16;  // SortSmem
 	static constexpr size_t O_WORK = O_SORT + SortSmem::BYTES;           // NPG x WorkSmem
 	static constexpr size_t BYTES = O_WORK + NPG * WorkSmem::BYTES;
 };
 
 
 // ---- kernel A: sort the prefix of every bin ----------------------------------------------------------------------
-__global__ void __launch_bounds__(FWD_GW * 32)
+__global__ void __launch_bounds__(FWD_GW * 32, 4)
 sort_prefix_kernel(int nbins, const uint32_t *__restrict__ loc, const uint32_t *__restrict__ binbase, uint4 *entries, uint4 *unsorted,
 		   uint32_t *__restrict__ sorted_end, uint32_t *__restrict__ alive, const FrameTotals *__restrict__ totals)
 {
@@ -330,7 +330,7 @@ render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 		       uint32_t *__restrict__ sorted_end, const uint32_t *__restrict__ alive, float4 *__restrict__ fin,
 		       uint4 *__restrict__ cta_prof, float *__restrict__ out_color, float *__restrict__ out_depth,
 		       float *__restrict__ out_occ, int sort_all, int full, const uint32_t *__restrict__ order,
-		       const FrameTotals *__restrict__ totals, unsigned *__restrict__ walk_stat)
+		       const FrameTotals *__restrict__ totals, unsigned *__restrict__ walk_stat, uint32_t *__restrict__ bin_cost)
 {
 	if (totals->overflow) return; // binning buffer too small for this frame: the host re-runs it (lgs_abi.cu)
 	using C = TailCfg<RB, ROWS>;
@@ -346,99 +346,80 @@ render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 	const long long clk0 = clock64();
 	const unsigned t0us = lgs_globaltimer_us();
 	extern __shared__ __align__(16) unsigned char smem[];
-	unsigned *sctl = reinterpret_cast<unsigned *>(smem + C::O_CTL); // [0] groups done, [1] warps finished, [2] chunks
-	uint4 *sdesc = reinterpret_cast<uint4 *>(smem + C::O_DESC);
-	uint2 *slots = reinterpret_cast<uint2 *>(smem + C::O_SLOT);
+	SortFeed *feed = reinterpret_cast<SortFeed *>(smem + C::O_FEED);
+	volatile SortFeed *vfeed = feed;
 	unsigned char *ss = smem + C::O_SORT;
 	unsigned *sloc = reinterpret_cast<unsigned *>(ss + SortSmem::LOC);
-	const unsigned bar_full = lgs_smem_addr(smem + C::O_BAR), bar_empty = bar_full + 8 * FWD_NSLOT;
 	for (int i = tid; i < LGS_NB; i += NT) sloc[i] = loc[(size_t)bin * LGS_NB + i];
 	if (tid == 0) {
 		sloc[LGS_NB] = ntotal;
-		sctl[0] = 0; sctl[1] = 0; sctl[2] = 0;
-#pragma unroll
-		for (int s = 0; s < FWD_NSLOT; s++) {
-			lgs_mbar_init(bar_full + 8 * s, 32);         // all lanes of the sorter arrive
-			lgs_mbar_init(bar_empty + 8 * s, 32 * NPG);  // all lanes of every worker arrive
-		}
+		feed_init(feed, se0);
 		lgs_mbar_init(lgs_smem_addr(ss + SortSmem::BAR), 1); // landing buffers: one arrive.expect_tx + the bulk copy's bytes
 		lgs_mbar_init(lgs_smem_addr(ss + SortSmem::BAR) + 8, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	__syncthreads(); // the only CTA-wide barrier: from here on the warps only meet at the mbarriers
+	__syncthreads(); // the only CTA-wide barrier: from here on the warps only meet through the feed (lgs_sorter.cuh)
 
 	if (warp == NPG) {
 		// =============================== sorter warp ===============================
-		const volatile unsigned *vdone = sctl;
 		int k0 = 0;
 		while (k0 < LGS_NB && sloc[k0] < se0) k0++; // kernel A sorted whole segments: the prefix ends at a bucket boundary
-		unsigned it = 0;
-		const unsigned se = run_sorter<true, true>(
+		unsigned upto = se0;
+		const unsigned se = run_sorter<false, true>(
 			ss, unsorted + base, entries + base, ntotal, k0, lane,
-			[&](unsigned) { return sort_all || vdone[0] < (unsigned)NPG; },
+			[&](unsigned) { return sort_all || vfeed->ndone < (unsigned)NPG; },
 			[&]() {
-				const unsigned slot = it % FWD_NSLOT, par = (it / FWD_NSLOT) & 1u;
-				lgs_mbar_wait(bar_empty + 8 * slot, par ^ 1u); // every worker has scanned the slot's previous contents
-				return slots + slot * FWD_CAP;
+				if (!sort_all) feed_wait_window(vfeed, upto, NPG, lane);
+				return (uint2 *)nullptr;
 			},
 			[&](unsigned pos0, int m) {
-				const unsigned slot = it % FWD_NSLOT;
-				if (lane == 0) sdesc[slot] = make_uint4(pos0, (unsigned)m, 0u, 0u);
-				__syncwarp();
-				lgs_mbar_arrive(bar_full + 8 * slot);
-				it++;
+				upto = pos0 + (unsigned)m;
+				feed_publish(vfeed, upto, lane);
 			});
-		{ // end marker
-			const unsigned slot = it % FWD_NSLOT, par = (it / FWD_NSLOT) & 1u;
-			lgs_mbar_wait(bar_empty + 8 * slot, par ^ 1u);
-			if (lane == 0) {
-				sdesc[slot] = make_uint4(0u, 0u, 1u, 0u);
-				sorted_end[bin] = max(se, se0);
-			}
-			__syncwarp();
-			lgs_mbar_arrive(bar_full + 8 * slot);
+		if (lane == 0) {
+			sorted_end[bin] = max(se, se0);
+			if (bin_cost) bin_cost[bin] = max(se, se0); // how far this bin was walked: the next frame's launch order (lgs_bin.cu)
 		}
+		feed_finish(vfeed, lane);
 	} else {
 		// =============================== worker warp: pixel group `warp`, resumed from kernel B's state ===============
 		GroupWorker w;
-		w.init(smem + C::O_WORK + (size_t)warp * WorkSmem::BYTES, g, RB, ROWS, bin, warp, lane, beams, rec, entries + base, !full, final_T,
+		uint4 *ebin = entries + base;
+		w.init(smem + C::O_WORK + (size_t)warp * WorkSmem::BYTES, g, RB, ROWS, bin, warp, lane, beams, rec, ebin, !full, final_T,
 		       n_contrib, fin);
-		bool gdone = w.live == 0;
-		if (gdone && lane == 0) atomicAdd(&sctl[0], 1u);
-		unsigned it = 0;
-		for (;;) {
-			const unsigned slot = it % FWD_NSLOT, par = (it / FWD_NSLOT) & 1u;
-			lgs_mbar_wait(bar_full + 8 * slot, par);
-			const uint4 d = sdesc[slot];
-			if (d.z) break; // end marker
-			if (!gdone) {
-				const uint2 *so = slots + slot * FWD_CAP;
-				const int m = (int)d.y;
-				for (int j0 = 0; j0 < m && w.live; j0 += 32) {
-					const int j = j0 + lane;
-					uint2 e = make_uint2(0u, 0u);
-					if (j < m) e = so[j];
-					w.scan32(e.x, e.y, d.x + (unsigned)j);
-				}
-				if (w.live == 0) {
-					gdone = true;
-					if (lane == 0) atomicAdd(&sctl[0], 1u);
-				}
+		unsigned pos = se0;
+		while (w.live) {
+			const unsigned avail = feed_wait(vfeed, pos); // > pos, or pos once the sorter has stopped there
+			if (avail <= pos) break;
+			uint4 enext = make_uint4(0u, 0u, 0u, 0u);
+			if (pos + (unsigned)lane < avail) enext = feed_load(ebin + pos + lane);
+			for (unsigned j0 = pos; j0 < avail && w.live; j0 += 32) {
+				const uint4 e = enext; // (lanes beyond the sorted part hold zeros: empty y range)
+				const unsigned jn = j0 + 32 + (unsigned)lane;
+				enext = make_uint4(0u, 0u, 0u, 0u);
+				if (jn < avail) enext = feed_load(ebin + jn);
+				w.scan32(e.y, e.z, j0 + (unsigned)lane);
+				if (lane == 0) vfeed->prog[warp] = min(j0 + 32u, avail);
 			}
-			__syncwarp();
-			lgs_mbar_arrive(bar_empty + 8 * slot);
-			it++;
+			pos = avail;
 		}
-		if (!gdone) w.flush();
-		if (lane == 0 && w.nchunks) {
-			atomicAdd(&sctl[2], w.nchunks);
-			if (walk_stat) atomicMax(walk_stat, w.nchunks * (2 / ROWS)); // in two-row-worker units whatever the worker shape
+		if (lane == 0) {
+			vfeed->prog[warp] = 0xffffffffu;
+			if (w.live == 0) atomicAdd(&feed->ndone, 1u);
+		}
+		if (w.live) w.flush(); // the list ended with pairs still queued
+		if (lane == 0) {
+			if (w.live) atomicAdd(&feed->ndone, 1u);
+			if (w.nchunks) {
+				atomicAdd(&feed->nchunks, w.nchunks);
+				if (walk_stat) atomicMax(walk_stat, w.nchunks * (2 / ROWS)); // in two-row-worker units whatever the worker shape
+			}
 		}
 		w.store(g, bg, final_T, n_contrib, fin, out_color, out_depth, out_occ);
 	}
 	__syncwarp();
-	if (lane == 0 && atomicAdd(&sctl[1], 1u) == (unsigned)C::NW - 1u) // last warp out: CTA diagnostics
-		cta_prof[bin] = make_uint4(t0us, (unsigned)(clock64() - clk0), lgs_smid(), sctl[2]);
+	if (lane == 0 && atomicAdd(&feed->nfin, 1u) == (unsigned)C::NW - 1u) // last warp out: CTA diagnostics
+		cta_prof[bin] = make_uint4(t0us, (unsigned)(clock64() - clk0), lgs_smid(), vfeed->nchunks);
 }
 
 // ---- kernel P: the same pass with evaluate and blend on DIFFERENT warps ---------------------------------------------------
@@ -765,7 +746,7 @@ render_fwd_pipe_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 template <int RB>
 void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries, uint4 *unsorted, const float *bg,
 		const float *beams, float *out_color, float *out_depth, float *out_occ, int sort_all, int split, unsigned *walk_stat,
-		cudaStream_t st)
+		uint32_t *bin_cost, cudaStream_t st)
 {
 	using C = TailCfg<RB>;
 	constexpr int NPG = C::NPG;
@@ -782,7 +763,7 @@ void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uin
 		cudaFuncSetAttribute(render_fwd_tail_kernel<RB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C1::BYTES);
 		render_fwd_tail_kernel<RB, 1><<<g.nbins, C1::NT, C1::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, unsorted, bg, beams, ip.final_T,
 										  ip.n_contrib, ip.sorted_end, ip.alive, ip.fin, ip.cta_prof, out_color,
-										  out_depth, out_occ, sort_all, 1, gp.order, gp.totals, walk_stat);
+										  out_depth, out_occ, sort_all, 1, gp.order, gp.totals, walk_stat, bin_cost);
 		return;
 	}
 	cudaFuncSetAttribute(render_fwd_tail_kernel<RB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
@@ -797,20 +778,20 @@ void launch_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uin
 	}
 	render_fwd_tail_kernel<RB, 2><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, entries, unsorted, bg, beams, ip.final_T,
 								     ip.n_contrib, ip.sorted_end, ip.alive, ip.fin, ip.cta_prof, out_color,
-								     out_depth, out_occ, sort_all, split ? 0 : 1, gp.order, gp.totals, walk_stat);
+								     out_depth, out_occ, sort_all, split ? 0 : 1, gp.order, gp.totals, walk_stat, bin_cost);
 }
 
 } // namespace
 
 void lgs_launch_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const ImagePtrs &ip, uint4 *entries, uint4 *unsorted,
 			   const float *bg, const float *beams, float *out_color, float *out_depth, float *out_occ,
-			   int sort_all, int split, unsigned *walk_stat, cudaStream_t st)
+			   int sort_all, int split, unsigned *walk_stat, uint32_t *bin_cost, cudaStream_t st)
 {
 	switch (g.RB) {
-	case 1: launch_fwd<1>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
-	case 2: launch_fwd<2>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
-	case 4: launch_fwd<4>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
-	case 8: launch_fwd<8>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
-	default: launch_fwd<16>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, st); break;
+	case 1: launch_fwd<1>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, bin_cost, st); break;
+	case 2: launch_fwd<2>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, bin_cost, st); break;
+	case 4: launch_fwd<4>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, bin_cost, st); break;
+	case 8: launch_fwd<8>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, bin_cost, st); break;
+	default: launch_fwd<16>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_depth, out_occ, sort_all, split, walk_stat, bin_cost, st); break;
 	}
 }

@@ -9,12 +9,15 @@
 
 namespace {
 
+
 #ifndef FWD_CAP
 #define FWD_CAP 512      // entries per segment (a single depth bucket larger than this is "oversized"); a multiple of 32
 #endif
 #define FWD_TARGET 128   // buckets are grouped until a segment has at least this many entries
 #define FWD_NSUB 256     // sub-buckets of the counting sort
-#define FWD_NSLOT 2      // kernel C's ring depth: how far the sorter may run ahead of the slowest worker
+#ifndef FWD_NSLOT
+#define FWD_NSLOT 2      // ring depth: how many sorted segments the sorter may run ahead of the slowest worker
+#endif
 #define FWD_QCAP 128     // pair queue ring (needs 31 + 64)
 #define FWD_TLD 33       // alpha tile row stride (floats): conflict-free for lanes = pairs stores
 #define FWD_PER (FWD_CAP / 32) // entries per sorter lane
@@ -24,10 +27,10 @@ struct SortSmem {
 	static constexpr size_t BAR = 0;                           // 2 mbarriers: landing buffers
 	static constexpr size_t LOC = 16;                          // bucket offsets of the bin (LGS_NB + 1)
 	static constexpr size_t RAW = (LOC + 4 * (LGS_NB + 1) + 15) / 16 * 16; // 2 x uint4 [CAP] landing buffers of the bulk copies
-	static constexpr size_t BKEY = RAW + 2 * 16 * FWD_CAP;     // sub-bucketed keys / values
-	static constexpr size_t BVAL = BKEY + 8 * FWD_CAP;
-	static constexpr size_t HIST = BVAL + 4 * FWD_CAP;         // NSUB + 1 counters -> sub-bucket starts
-	static constexpr size_t PH1 = (HIST + 4 * (FWD_NSUB + 1) + 15) / 16 * 16; // oversized buckets: sub-range starts, level 1 / level 2
+	static constexpr size_t BKEY = RAW + 2 * 16 * FWD_CAP;     // keys grouped by sub-bucket
+	static constexpr size_t CODE = BKEY + 8 * FWD_CAP;         // u32 per raw entry: sub-bucket | arrival rank inside it << 16
+	static constexpr size_t HIST = CODE + 4 * FWD_CAP;         // NSUB + 1 counters -> sub-bucket starts, padded (sort_hix)
+	static constexpr size_t PH1 = (HIST + 4 * (FWD_NSUB + FWD_NSUB / 8 + 1) + 15) / 16 * 16; // oversized buckets: sub-range starts, level 1 / level 2
 	static constexpr size_t PH2 = PH1 + 4 * (FWD_NSUB + 4);
 	static constexpr size_t BYTES = (PH2 + 4 * (FWD_NSUB + 4) + 15) / 16 * 16;
 };
@@ -76,81 +79,125 @@ __device__ void warp_bitonic_sort_global(uint4 *e, int n, int lane)
 // Sort the m <= FWD_CAP entries of a segment, already in shared memory (`raw`, landed there by a bulk copy), on
 // (depth bits << 32 | idx) with one warp: counting sort on a monotone quantisation of the depth bits (FWD_NSUB
 // sub-buckets over the segment's own range), then rank inside the sub-bucket by the full key (keys are unique: the
-// Gaussian index is part of the key).  Every pass is unrolled over the lane's FWD_PER entries so that its shared-memory
-// loads and atomics are in flight together; the sub-bucket and the rank the counting atomic returned stay in registers.
+// Gaussian index is part of the key).  The sorter is the critical path of a bin whose rays never saturate (its workers
+// wait for it), so every pass handles SORT_G entries of a lane together -- loads, the counting atomics and the rank loops
+// of the group are in flight at once -- and the counters are padded so that the prefix pass is free of bank conflicts.
 // The sorted entries are written back to `seg` in global memory (spare word = 0: the workers OR their blended-row flags
 // into it; the backward pass replays them) and, when SLOT, as (idx, y-range) to the ring slot `so`.
+#define SORT_G 4
+__device__ __forceinline__ int sort_hix(int c) { return c + (c >> 3); } // counter c lives at hist[c + c / 8]: a lane's run of 8 has stride 9
 template <bool SLOT>
 __device__ __forceinline__ void warp_sort_segment(uint4 *seg, const uint4 *raw, int m, uint2 *so, unsigned long long *bkey,
-						  unsigned *bval, unsigned *hist, int lane)
+						  unsigned *code, unsigned *hist, int lane)
 {
+	static_assert(FWD_PER % SORT_G == 0 && FWD_NSUB == 256, "sorter geometry");
+	constexpr int HWORDS = FWD_NSUB + FWD_NSUB / 8 + 1;
+#pragma unroll
+	for (int t = 0; t < (HWORDS + 31) / 32; t++)
+		if (lane + 32 * t < HWORDS) hist[lane + 32 * t] = 0;
 	unsigned dmin = 0xffffffffu, dmax = 0u;
 #pragma unroll
-	for (int t = 0; t < FWD_PER; t++) {
-		if (32 * t >= m) break;
-		const int i = lane + 32 * t;
-		if (i < m) {
-			const unsigned d = raw[i].x;
-			dmin = min(dmin, d);
-			dmax = max(dmax, d);
+	for (int t0 = 0; t0 < FWD_PER; t0 += SORT_G) {
+		if (32 * t0 >= m) break;
+		unsigned d[SORT_G];
+#pragma unroll
+		for (int u = 0; u < SORT_G; u++) {
+			const int i = lane + 32 * (t0 + u);
+			d[u] = raw[i < m ? i : 0].x;
+		}
+#pragma unroll
+		for (int u = 0; u < SORT_G; u++) {
+			dmin = min(dmin, d[u]); // (entry 0 stands in for a lane without an entry: it belongs to the segment)
+			dmax = max(dmax, d[u]);
 		}
 	}
 	dmin = __reduce_min_sync(0xffffffffu, dmin);
 	dmax = __reduce_max_sync(0xffffffffu, dmax);
-#pragma unroll
-	for (int t = 0; t < (FWD_NSUB + 32) / 32; t++)
-		if (lane + 32 * t <= FWD_NSUB) hist[lane + 32 * t] = 0;
 	__syncwarp();
 	const float scale = (float)FWD_NSUB / ((float)(dmax - dmin) + 1.0f);
 	// monotone in d: int -> float rounding, a positive scale and truncation all preserve order
 	auto subof = [&](unsigned d) { return min((int)((float)(d - dmin) * scale), FWD_NSUB - 1); };
-	unsigned code[FWD_PER]; // sub-bucket | rank inside it << 16 (arrival order)
 #pragma unroll
-	for (int t = 0; t < FWD_PER; t++) {
-		if (32 * t >= m) break;
-		const int i = lane + 32 * t;
-		if (i < m) {
-			const int sb = subof(raw[i].x);
-			code[t] = (unsigned)sb | (atomicAdd(&hist[sb], 1u) << 16);
+	for (int t0 = 0; t0 < FWD_PER; t0 += SORT_G) {
+		if (32 * t0 >= m) break;
+		int sb[SORT_G];
+#pragma unroll
+		for (int u = 0; u < SORT_G; u++) {
+			const int i = lane + 32 * (t0 + u);
+			sb[u] = subof(raw[i < m ? i : 0].x);
 		}
+		unsigned old[SORT_G];
+#pragma unroll
+		for (int u = 0; u < SORT_G; u++) {
+			old[u] = 0;
+			if (lane + 32 * (t0 + u) < m) old[u] = atomicAdd(&hist[sort_hix(sb[u])], 1u);
+		}
+#pragma unroll
+		for (int u = 0; u < SORT_G; u++) code[lane + 32 * (t0 + u)] = (unsigned)sb[u] | (old[u] << 16); // (own entries only: no sync needed)
 	}
 	__syncwarp();
-	{ // exclusive prefix in place: lane owns FWD_NSUB / 32 consecutive counters; hist[NSUB] = m
+	{ // exclusive prefix in place: lane owns 8 consecutive counters (words 9 * lane ..); counter NSUB = m
 		constexpr int PER = FWD_NSUB / 32;
 		unsigned v[PER], sum = 0;
 #pragma unroll
-		for (int t = 0; t < PER; t++) { v[t] = hist[lane * PER + t]; sum += v[t]; }
+		for (int t = 0; t < PER; t++) { v[t] = hist[lane * (PER + 1) + t]; sum += v[t]; }
 		unsigned run = warp_excl_scan_u32(sum, lane);
 #pragma unroll
-		for (int t = 0; t < PER; t++) { hist[lane * PER + t] = run; run += v[t]; }
-		if (lane == 31) hist[FWD_NSUB] = run;
+		for (int t = 0; t < PER; t++) { hist[lane * (PER + 1) + t] = run; run += v[t]; }
+		if (lane == 31) hist[sort_hix(FWD_NSUB)] = run;
 	}
 	__syncwarp();
 #pragma unroll
-	for (int t = 0; t < FWD_PER; t++) {
-		if (32 * t >= m) break;
-		const int i = lane + 32 * t;
-		if (i < m) {
-			const uint4 e = raw[i];
-			const unsigned p = hist[code[t] & 0xffffu] + (code[t] >> 16);
-			bkey[p] = ((unsigned long long)e.x << 32) | e.y;
-			bval[p] = e.z;
+	for (int t0 = 0; t0 < FWD_PER; t0 += SORT_G) {
+		if (32 * t0 >= m) break;
+		uint2 kk[SORT_G];
+		unsigned cd[SORT_G], st[SORT_G];
+#pragma unroll
+		for (int u = 0; u < SORT_G; u++) {
+			const int i = lane + 32 * (t0 + u);
+			kk[u] = *reinterpret_cast<const uint2 *>(raw + (i < m ? i : 0));
+			cd[u] = code[lane + 32 * (t0 + u)];
 		}
+#pragma unroll
+		for (int u = 0; u < SORT_G; u++) st[u] = hist[sort_hix((int)(cd[u] & 0xffffu))];
+#pragma unroll
+		for (int u = 0; u < SORT_G; u++)
+			if (lane + 32 * (t0 + u) < m) bkey[st[u] + (cd[u] >> 16)] = ((unsigned long long)kk[u].x << 32) | kk[u].y;
 	}
 	__syncwarp();
 #pragma unroll
-	for (int t = 0; t < FWD_PER; t++) {
-		if (32 * t >= m) break;
-		const int p = lane + 32 * t;
-		if (p < m) {
-			const unsigned long long key = bkey[p];
-			const int sb = subof((unsigned)(key >> 32));
-			const int lo = (int)hist[sb], hi = (int)hist[sb + 1];
-			int r = lo;
-			for (int j = lo; j < hi; j++) r += bkey[j] < key;
-			const unsigned v = bval[p];
-			if (SLOT) so[r] = make_uint2((unsigned)key, v);
-			seg[r] = make_uint4((unsigned)(key >> 32), (unsigned)key, v, 0u);
+	for (int t0 = 0; t0 < FWD_PER; t0 += SORT_G) {
+		if (32 * t0 >= m) break;
+		unsigned long long key[SORT_G];
+		unsigned yp[SORT_G];
+		int lo[SORT_G], cnt[SORT_G], r[SORT_G];
+		int mc = 0;
+#pragma unroll
+		for (int u = 0; u < SORT_G; u++) {
+			const int i = lane + 32 * (t0 + u);
+			const uint4 e = raw[i < m ? i : 0];
+			const int sb = (int)(code[lane + 32 * (t0 + u)] & 0xffffu);
+			key[u] = ((unsigned long long)e.x << 32) | e.y;
+			yp[u] = e.z;
+			lo[u] = (int)hist[sort_hix(sb)];
+			cnt[u] = i < m ? (int)hist[sort_hix(sb + 1)] - lo[u] : 0;
+			r[u] = lo[u];
+			mc = max(mc, cnt[u]);
+		}
+		mc = __reduce_max_sync(0xffffffffu, mc);
+		if (mc > 1) { // (a sub-bucket of one: the entry's rank is the sub-bucket's start)
+			for (int j = 0; j < mc; j++) {
+#pragma unroll
+				for (int u = 0; u < SORT_G; u++)
+					if (j < cnt[u]) r[u] += bkey[lo[u] + j] < key[u];
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < SORT_G; u++) {
+			if (lane + 32 * (t0 + u) < m) {
+				if (SLOT) so[r[u]] = make_uint2((unsigned)key[u], yp[u]);
+				seg[r[u]] = make_uint4((unsigned)(key[u] >> 32), (unsigned)key[u], yp[u], 0u);
+			}
 		}
 	}
 }
@@ -238,7 +285,7 @@ __device__ __forceinline__ unsigned run_sorter(unsigned char *ss, uint4 *ubin, u
 	const unsigned *sloc = reinterpret_cast<const unsigned *>(ss + SortSmem::LOC);
 	uint4 *raw = reinterpret_cast<uint4 *>(ss + SortSmem::RAW);
 	unsigned long long *bkey = reinterpret_cast<unsigned long long *>(ss + SortSmem::BKEY);
-	unsigned *bval = reinterpret_cast<unsigned *>(ss + SortSmem::BVAL);
+	unsigned *code = reinterpret_cast<unsigned *>(ss + SortSmem::CODE);
 	unsigned *hist = reinterpret_cast<unsigned *>(ss + SortSmem::HIST);
 	unsigned *ph1 = reinterpret_cast<unsigned *>(ss + SortSmem::PH1), *ph2 = reinterpret_cast<unsigned *>(ss + SortSmem::PH2);
 	const unsigned bar_raw = lgs_smem_addr(ss + SortSmem::BAR);
@@ -262,7 +309,7 @@ __device__ __forceinline__ unsigned run_sorter(unsigned char *ss, uint4 *ubin, u
 		uint4 *rb = raw + buf * FWD_CAP;
 		for (int i = lane; i < m; i += 32) rb[i] = from[i];
 		__syncwarp();
-		warp_sort_segment<SLOT>(sbin + pos, rb, m, so, bkey, bval, hist, lane);
+		warp_sort_segment<SLOT>(sbin + pos, rb, m, so, bkey, code, hist, lane);
 		__syncwarp();
 		publish(pos, m);
 		sorted_to = pos + (unsigned)m;
@@ -280,7 +327,7 @@ __device__ __forceinline__ unsigned run_sorter(unsigned char *ss, uint4 *ubin, u
 		if (nn && nn <= FWD_CAP) { prefetch(s0n, nn, buf ^ 1u); inflight_next = true; } // overlaps the sort below
 		if (!oversized) {
 			uint2 *so = acquire_slot();
-			warp_sort_segment<SLOT>(sbin + s0, raw + buf * FWD_CAP, (int)n, so, bkey, bval, hist, lane);
+			warp_sort_segment<SLOT>(sbin + s0, raw + buf * FWD_CAP, (int)n, so, bkey, code, hist, lane);
 			publish(s0, (int)n);
 			sorted_to = s0 + n;
 		} else {
@@ -335,6 +382,82 @@ __device__ __forceinline__ unsigned run_sorter(unsigned char *ss, uint4 *ubin, u
 	}
 	if (inflight) lgs_mbar_wait(bar_raw + 8 * buf, (rawpar >> buf) & 1u); // never leave with a bulk copy in flight
 	return (n || stopped) ? sorted_to : ntotal;
+}
+
+
+// ---- sorter -> workers hand-over of one bin ---------------------------------------------------------------------------
+// The sorted list itself (global memory, `sbin`) is the channel: the sorter publishes how far the list is sorted, every
+// worker warp reads the entries at its own pace (ld.global.cg: they were written by another warp of the same CTA a moment
+// ago and sit in L2) and publishes how far it has scanned.  Nobody waits for a slot to be released: a worker that has a
+// chunk to composite does not hold up the others, and the sorter only pauses when it is a whole window ahead of the
+// slowest live worker -- laziness: entries nobody will read are not sorted -- where the window grows with the depth the
+// bin has already been walked to (rays that are still alive after thousands of entries are not about to stop).
+#define FEED_WINDOW 640u
+struct SortFeed { // in shared memory
+	unsigned sorted;   // entries [0, sorted) of the bin's list are sorted and visible to the CTA
+	unsigned end;      // 1: the sorter has stopped, `sorted` is final
+	unsigned ndone;    // workers whose pixels have all terminated
+	unsigned nfin;     // warps that have left the kernel (diagnostics)
+	unsigned nchunks;  // chunks composited by the workers (diagnostics)
+	unsigned pad[3];
+	unsigned prog[16]; // per worker: list position it has scanned up to (0xffffffff: all its pixels have terminated)
+};
+__device__ __forceinline__ void feed_init(SortFeed *f, unsigned sorted0)
+{
+	f->sorted = sorted0; f->end = 0; f->ndone = 0; f->nfin = 0; f->nchunks = 0;
+	for (int i = 0; i < 16; i++) f->prog[i] = sorted0;
+}
+// sorter: may the next segment (the list is sorted up to `sorted_to`) be sorted now?  Waits while it is a window ahead.
+__device__ __forceinline__ void feed_wait_window(volatile SortFeed *f, unsigned sorted_to, int nworkers, int lane)
+{
+	const long long t0 = clock64();
+	for (;;) {
+		unsigned p = lane < nworkers ? f->prog[lane] : 0xffffffffu;
+		p = __reduce_min_sync(0xffffffffu, p);
+		if (p == 0xffffffffu || sorted_to - min(p, sorted_to) < max(FEED_WINDOW, p << 1)) return;
+		__nanosleep(200);
+		if (clock64() - t0 > 4000000000ll) __trap(); // a protocol error must not hang the GPU
+	}
+}
+// sorter: the list is now sorted up to `sorted_to` (all lanes call; their global stores become visible before the counter)
+__device__ __forceinline__ void feed_publish(volatile SortFeed *f, unsigned sorted_to, int lane)
+{
+	__threadfence_block();
+	__syncwarp();
+	if (lane == 0) {
+		__threadfence_block();
+		f->sorted = sorted_to;
+	}
+}
+__device__ __forceinline__ void feed_finish(volatile SortFeed *f, int lane)
+{
+	__syncwarp();
+	if (lane == 0) {
+		__threadfence_block();
+		f->end = 1u;
+	}
+}
+// worker: how far is the list sorted?  Returns a position > pos, or pos itself once the sorter has stopped there.
+__device__ __forceinline__ unsigned feed_wait(volatile SortFeed *f, unsigned pos)
+{
+	unsigned a = f->sorted;
+	if (a <= pos) {
+		const long long t0 = clock64();
+		for (;;) {
+			const unsigned e = f->end; // read before `sorted`: once set, the value read next is final
+			a = f->sorted;
+			if (a > pos || e) break;
+			__nanosleep(100);
+			if (clock64() - t0 > 4000000000ll) __trap();
+		}
+	}
+	a = __shfl_sync(0xffffffffu, a, 0);
+	__threadfence_block();
+	return a;
+}
+__device__ __forceinline__ uint4 feed_load(const uint4 *p)
+{
+	return __ldcg(p);
 }
 
 } // namespace

@@ -45,11 +45,8 @@ template <int RB> struct SFwdCfg {
 	static constexpr int NPG = RB >= 2 ? RB / 2 : 1; // worker warps
 	static constexpr int NW = NPG + 1;               // + the sorter warp (last)
 	static constexpr int NT = NW * 32;
-	static constexpr size_t O_BAR = 0;                                   // full[NSLOT], empty[NSLOT] mbarriers
-	static constexpr size_t O_CTL = O_BAR + 8 * 2 * FWD_NSLOT;           // groups done
-	static constexpr size_t O_DESC = O_CTL + 16;                         // uint4 per slot: {list position, count, end, -}
-	static constexpr size_t O_SLOT = O_DESC + 16 * FWD_NSLOT;            // uint2 (id, y0 | y1 << 16) per sorted entry
-	static constexpr size_t O_SORT = O_SLOT + 8 * FWD_CAP * FWD_NSLOT;   // SortSmem
+	static constexpr size_t O_FEED = 0;                                  // SortFeed
+	static constexpr size_t O_SORT = (sizeof(SortFeed) + 15) / 16 * 16;  // SortSmem
 	static constexpr size_t O_WORK = O_SORT + SortSmem::BYTES;           // NPG x SWorkSmem
 	static constexpr size_t BYTES = O_WORK + NPG * SWorkSmem::BYTES;
 };
@@ -274,7 +271,7 @@ __global__ void __launch_bounds__(SFwdCfg<RB>::NT, 4)
 surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32_t *__restrict__ loc,
 			 const uint32_t *__restrict__ binbase, const uint32_t *__restrict__ order, uint4 *entries, uint4 *unsorted,
 			 const float *__restrict__ bg, const float *__restrict__ beams, SurfelImagePtrs ip, float *__restrict__ out_color,
-			 float *__restrict__ out_others, int sort_all, const FrameTotals *__restrict__ totals)
+			 float *__restrict__ out_others, int sort_all, const FrameTotals *__restrict__ totals, uint32_t *__restrict__ bin_cost)
 {
 	if (totals->overflow) return; // binning buffer too small for this frame: the host re-runs it (lgs_abi.cu)
 	using C = SFwdCfg<RB>;
@@ -282,87 +279,65 @@ surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 	const int bin = (int)order[blockIdx.x], tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const unsigned base = binbase[bin], ntotal = binbase[bin + 1] - base;
 	extern __shared__ __align__(16) unsigned char smem[];
-	unsigned *sctl = reinterpret_cast<unsigned *>(smem + C::O_CTL); // [0] groups done
-	uint4 *sdesc = reinterpret_cast<uint4 *>(smem + C::O_DESC);
-	uint2 *slots = reinterpret_cast<uint2 *>(smem + C::O_SLOT);
+	SortFeed *feed = reinterpret_cast<SortFeed *>(smem + C::O_FEED);
+	volatile SortFeed *vfeed = feed;
 	unsigned char *ss = smem + C::O_SORT;
 	unsigned *sloc = reinterpret_cast<unsigned *>(ss + SortSmem::LOC);
-	const unsigned bar_full = lgs_smem_addr(smem + C::O_BAR), bar_empty = bar_full + 8 * FWD_NSLOT;
 	for (int i = tid; i < LGS_NB; i += NT) sloc[i] = loc[(size_t)bin * LGS_NB + i];
 	if (tid == 0) {
 		sloc[LGS_NB] = ntotal;
-		sctl[0] = 0;
-#pragma unroll
-		for (int s = 0; s < FWD_NSLOT; s++) {
-			lgs_mbar_init(bar_full + 8 * s, 32);         // all lanes of the sorter arrive
-			lgs_mbar_init(bar_empty + 8 * s, 32 * NPG);  // all lanes of every worker arrive
-		}
+		feed_init(feed, 0u);
 		lgs_mbar_init(lgs_smem_addr(ss + SortSmem::BAR), 1); // landing buffers: one arrive.expect_tx + the bulk copy's bytes
 		lgs_mbar_init(lgs_smem_addr(ss + SortSmem::BAR) + 8, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	__syncthreads(); // the only CTA-wide barrier: from here on the warps only meet at the mbarriers
+	__syncthreads(); // the only CTA-wide barrier: from here on the warps only meet through the feed (lgs_sorter.cuh)
 
 	if (warp == NPG) {
 		// =============================== sorter warp ===============================
-		const volatile unsigned *vdone = sctl;
-		unsigned it = 0;
-		const unsigned se = run_sorter<true, true>(
+		unsigned upto = 0;
+		const unsigned se = run_sorter<false, true>(
 			ss, unsorted + base, entries + base, ntotal, 0, lane,
-			[&](unsigned) { return sort_all || vdone[0] < (unsigned)NPG; },
+			[&](unsigned) { return sort_all || vfeed->ndone < (unsigned)NPG; },
 			[&]() {
-				const unsigned slot = it % FWD_NSLOT, par = (it / FWD_NSLOT) & 1u;
-				lgs_mbar_wait(bar_empty + 8 * slot, par ^ 1u); // every worker has scanned the slot's previous contents
-				return slots + slot * FWD_CAP;
+				if (!sort_all) feed_wait_window(vfeed, upto, NPG, lane);
+				return (uint2 *)nullptr;
 			},
 			[&](unsigned pos0, int m) {
-				const unsigned slot = it % FWD_NSLOT;
-				if (lane == 0) sdesc[slot] = make_uint4(pos0, (unsigned)m, 0u, 0u);
-				__syncwarp();
-				lgs_mbar_arrive(bar_full + 8 * slot);
-				it++;
+				upto = pos0 + (unsigned)m;
+				feed_publish(vfeed, upto, lane);
 			});
-		{ // end marker
-			const unsigned slot = it % FWD_NSLOT, par = (it / FWD_NSLOT) & 1u;
-			lgs_mbar_wait(bar_empty + 8 * slot, par ^ 1u);
-			if (lane == 0) {
-				sdesc[slot] = make_uint4(0u, 0u, 1u, 0u);
-				ip.sorted_end[bin] = se;
-			}
-			__syncwarp();
-			lgs_mbar_arrive(bar_full + 8 * slot);
+		if (lane == 0) {
+			ip.sorted_end[bin] = se;
+			if (bin_cost) bin_cost[bin] = se; // how far this bin was walked: the next frame's launch order (lgs_bin.cu)
 		}
+		feed_finish(vfeed, lane);
 	} else {
 		// =============================== worker warp: pixel group `warp` ===============================
 		SurfelWorker w;
-		w.init(smem + C::O_WORK + (size_t)warp * SWorkSmem::BYTES, g, RB, bin, warp, lane, beams, rec, entries + base);
-		bool gdone = w.live == 0;
-		if (gdone && lane == 0) atomicAdd(&sctl[0], 1u);
-		unsigned it = 0;
-		for (;;) {
-			const unsigned slot = it % FWD_NSLOT, par = (it / FWD_NSLOT) & 1u;
-			lgs_mbar_wait(bar_full + 8 * slot, par);
-			const uint4 d = sdesc[slot];
-			if (d.z) break; // end marker
-			if (!gdone) {
-				const uint2 *so = slots + slot * FWD_CAP;
-				const int m = (int)d.y;
-				for (int j0 = 0; j0 < m && w.live; j0 += 32) {
-					const int j = j0 + lane;
-					uint2 e = make_uint2(0u, 0u);
-					if (j < m) e = so[j];
-					w.scan32(e.x, e.y, d.x + (unsigned)j);
-				}
-				if (w.live == 0) {
-					gdone = true;
-					if (lane == 0) atomicAdd(&sctl[0], 1u);
-				}
+		uint4 *ebin = entries + base;
+		w.init(smem + C::O_WORK + (size_t)warp * SWorkSmem::BYTES, g, RB, bin, warp, lane, beams, rec, ebin);
+		unsigned pos = 0;
+		while (w.live) {
+			const unsigned avail = feed_wait(vfeed, pos); // > pos, or pos once the sorter has stopped there
+			if (avail <= pos) break;
+			uint4 enext = make_uint4(0u, 0u, 0u, 0u);
+			if (pos + (unsigned)lane < avail) enext = feed_load(ebin + pos + lane);
+			for (unsigned j0 = pos; j0 < avail && w.live; j0 += 32) {
+				const uint4 e = enext; // (lanes beyond the sorted part hold zeros: empty y range)
+				const unsigned jn = j0 + 32 + (unsigned)lane;
+				enext = make_uint4(0u, 0u, 0u, 0u);
+				if (jn < avail) enext = feed_load(ebin + jn);
+				w.scan32(e.y, e.z, j0 + (unsigned)lane);
+				if (lane == 0) vfeed->prog[warp] = min(j0 + 32u, avail);
 			}
-			__syncwarp();
-			lgs_mbar_arrive(bar_empty + 8 * slot);
-			it++;
+			pos = avail;
 		}
-		if (!gdone) w.flush();
+		if (lane == 0) {
+			vfeed->prog[warp] = 0xffffffffu;
+			atomicAdd(&feed->ndone, 1u);
+		}
+		if (w.live) w.flush(); // the list ended with pairs still queued
 		w.store(g, bg, ip, out_color, out_others);
 	}
 }
@@ -689,26 +664,26 @@ surfel_render_bwd_kernel(FrameGeom g, int nunits, const float4 *__restrict__ rec
 
 template <int RB>
 void launch_sfwd(const FrameGeom &g, const GeomPtrs &gp, const SurfelImagePtrs &ip, uint4 *entries, uint4 *unsorted,
-		 const float *bg, const float *beams, float *out_color, float *out_others, int sort_all, cudaStream_t st)
+		 const float *bg, const float *beams, float *out_color, float *out_others, int sort_all, uint32_t *bin_cost, cudaStream_t st)
 {
 	using C = SFwdCfg<RB>;
 	// function attributes are per device: set on every call (a host-side table lookup), not once per process
 	cudaFuncSetAttribute(surfel_render_fwd_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES);
 	surfel_render_fwd_kernel<RB><<<g.nbins, C::NT, C::BYTES, st>>>(g, gp.rec, gp.loc, gp.binbase, gp.order, entries, unsorted, bg,
-									beams, ip, out_color, out_others, sort_all, gp.totals);
+									beams, ip, out_color, out_others, sort_all, gp.totals, bin_cost);
 }
 
 } // namespace
 
 void lgs_launch_surfel_render_fwd(const FrameGeom &g, const GeomPtrs &gp, const SurfelImagePtrs &ip, uint4 *entries,
 				  uint4 *unsorted, const float *bg, const float *beams, float *out_color, float *out_others,
-				  int sort_all, cudaStream_t st)
+				  int sort_all, uint32_t *bin_cost, cudaStream_t st)
 {
 	switch (g.RB) {
-	case 1: launch_sfwd<1>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_others, sort_all, st); break;
-	case 2: launch_sfwd<2>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_others, sort_all, st); break;
-	case 4: launch_sfwd<4>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_others, sort_all, st); break;
-	default: launch_sfwd<8>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_others, sort_all, st); break;
+	case 1: launch_sfwd<1>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_others, sort_all, bin_cost, st); break;
+	case 2: launch_sfwd<2>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_others, sort_all, bin_cost, st); break;
+	case 4: launch_sfwd<4>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_others, sort_all, bin_cost, st); break;
+	default: launch_sfwd<8>(g, gp, ip, entries, unsorted, bg, beams, out_color, out_others, sort_all, bin_cost, st); break;
 	}
 }
 

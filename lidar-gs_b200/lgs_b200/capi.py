@@ -13,7 +13,7 @@ ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 _lib = None
 
 SYMBOLS = ["lgs_forward", "lgs_backward", "lgs_backward_scratch_bytes", "lgs_visible_filter", "lgs_mark_visible",
-           "lgs_set_rows_per_bin", "lgs_set_sort_all", "lgs_set_forward_split", "lgs_last_forward_mode", "lgs_last_longest_walk", "lgs_overflow_reruns", "lgs_set_capacity_hint", "lgs_timing_enable", "lgs_timing_collect", "lgs_last_num_instances", "lgs_launch_count",
+           "lgs_set_rows_per_bin", "lgs_set_sort_all", "lgs_set_forward_split", "lgs_set_order_history", "lgs_last_forward_mode", "lgs_last_longest_walk", "lgs_overflow_reruns", "lgs_set_capacity_hint", "lgs_timing_enable", "lgs_timing_collect", "lgs_last_num_instances", "lgs_launch_count",
            "lgs_last_error", "lgs_version",
            "lgs_surfel_forward", "lgs_surfel_backward", "lgs_surfel_backward_scratch_bytes", "lgs_surfel_visible_filter",
            "lgs_surfel_mark_visible", "lgs_backward_touched", "lgs_grad_pack_bytes", "lgs_grad_count", "lgs_grad_pack", "lgs_grad_scatter_add",
@@ -84,6 +84,7 @@ def load():
     L.lgs_set_rows_per_bin.argtypes = [i]
     L.lgs_set_sort_all.argtypes = [i]
     L.lgs_set_forward_split.argtypes = [i]
+    L.lgs_set_order_history.argtypes = [i]
     L.lgs_timing_enable.argtypes = [i]
     L.lgs_timing_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.lgs_last_num_instances.restype = C.c_longlong

@@ -416,6 +416,29 @@ def test_worker_shape_follows_the_longest_walk():
         L.lgs_set_forward_split(-1)
 
 
+def test_launch_order_history_is_only_a_hint():
+    """The compositing pass launches its bins in the order of the previous frame's walk depths (lgs_set_order_history): a
+    scheduling hint -- the images are bit-identical with the hint, without it, and when the previous frame was a different
+    scene of the same geometry."""
+    from lgs_b200 import capi
+    L = capi.load()
+    a = _scene(60000, 32, 512, 41, pose="random")
+    b = _scene(30000, 32, 512, 42, pose="identity")
+    try:
+        L.lgs_set_order_history(0)
+        ref_a, _ = util.run_abi(a)
+        ref_b, _ = util.run_abi(b)
+        L.lgs_set_order_history(1)
+        for sc, ref in ((a, ref_a), (a, ref_a), (b, ref_b), (a, ref_a), (b, ref_b), (b, ref_b)):
+            res, _ = util.run_abi(sc)
+            for k in ref:
+                if isinstance(ref[k], np.ndarray) and ref[k].dtype == np.float32 and k in ("color", "depth", "occ"):
+                    assert np.array_equal(res[k].view(np.uint32), ref[k].view(np.uint32)), k
+            assert np.array_equal(res["radii"], ref["radii"])
+    finally:
+        L.lgs_set_order_history(1)
+
+
 def _wall_scene(P, H, W, seed, r0=30.0, thickness=0.2, dup=0):
     """A surface at one range: every Gaussian within +-thickness/2 of a sphere of radius r0 around the sensor, so that each
     bin's list sits in ONE depth bucket (1.25 m wide) with far more entries than the sorter's shared-memory capacity; `dup`

@@ -10,8 +10,12 @@ sys.path.insert(0, ROOT)
 import bench
 POSE=int(sys.argv[1]) if len(sys.argv)>1 else 0
 sc["viewmatrix"]=bench.rank_pose(sc, POSE)
-for it in range(2):
+from lgs_b200 import capi
+L=capi.load()
+if len(sys.argv)>2: L.lgs_set_forward_split(int(sys.argv[2]))
+for it in range(4):
     res, fr = util.run_abi(sc, backward=False)
+print('pose',POSE,'forward mode',L.lgs_last_forward_mode(),'longest walk',L.lgs_last_longest_walk())
 H,W,P=sc["H"],sc["W"],sc["P"]
 v=frame_views(fr,P,H,W)
 nb=v["nbins"]
