@@ -391,14 +391,11 @@ render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 		while (w.live) {
 			const unsigned avail = feed_wait(vfeed, pos); // > pos, or pos once the sorter has stopped there
 			if (avail <= pos) break;
-			uint4 enext = make_uint4(0u, 0u, 0u, 0u);
-			if (pos + (unsigned)lane < avail) enext = feed_load(ebin + pos + lane);
+			uint2 enext = feed_load_idy(ebin, pos + (unsigned)lane, avail);
 			for (unsigned j0 = pos; j0 < avail && w.live; j0 += 32) {
-				const uint4 e = enext; // (lanes beyond the sorted part hold zeros: empty y range)
-				const unsigned jn = j0 + 32 + (unsigned)lane;
-				enext = make_uint4(0u, 0u, 0u, 0u);
-				if (jn < avail) enext = feed_load(ebin + jn);
-				w.scan32(e.y, e.z, j0 + (unsigned)lane);
+				const uint2 e = enext; // (lanes beyond the sorted part hold zeros: empty y range)
+				enext = feed_load_idy(ebin, j0 + 32u + (unsigned)lane, avail);
+				w.scan32(e.x, e.y, j0 + (unsigned)lane);
 				if (lane == 0) vfeed->prog[warp] = min(j0 + 32u, avail);
 			}
 			pos = avail;

@@ -455,9 +455,12 @@ __device__ __forceinline__ unsigned feed_wait(volatile SortFeed *f, unsigned pos
 	__threadfence_block();
 	return a;
 }
-__device__ __forceinline__ uint4 feed_load(const uint4 *p)
+// worker: (Gaussian index, y range) of the sorted entry at list position `pos` (zeros at or behind `avail`)
+__device__ __forceinline__ uint2 feed_load_idy(const uint4 *ebin, unsigned pos, unsigned avail)
 {
-	return __ldcg(p);
+	if (pos >= avail) return make_uint2(0u, 0u);
+	const uint4 e = __ldcg(ebin + pos);
+	return make_uint2(e.y, e.z);
 }
 
 } // namespace
