@@ -347,7 +347,6 @@ render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 	const unsigned t0us = lgs_globaltimer_us();
 	extern __shared__ __align__(16) unsigned char smem[];
 	SortFeed *feed = reinterpret_cast<SortFeed *>(smem + C::O_FEED);
-	volatile SortFeed *vfeed = feed;
 	unsigned char *ss = smem + C::O_SORT;
 	unsigned *sloc = reinterpret_cast<unsigned *>(ss + SortSmem::LOC);
 	for (int i = tid; i < LGS_NB; i += NT) sloc[i] = loc[(size_t)bin * LGS_NB + i];
@@ -367,20 +366,20 @@ render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 		unsigned upto = se0;
 		const unsigned se = run_sorter<false, true>(
 			ss, unsorted + base, entries + base, ntotal, k0, lane,
-			[&](unsigned) { return sort_all || vfeed->ndone < (unsigned)NPG; },
+			[&](unsigned) { return sort_all || !feed_all_done(feed, NPG, lane); },
 			[&]() {
-				if (!sort_all) feed_wait_window(vfeed, upto, NPG, lane);
+				if (!sort_all) feed_wait_window(feed, upto, NPG, lane);
 				return (uint2 *)nullptr;
 			},
 			[&](unsigned pos0, int m) {
 				upto = pos0 + (unsigned)m;
-				feed_publish(vfeed, upto, lane);
+				feed_publish(feed, upto, lane);
 			});
 		if (lane == 0) {
 			sorted_end[bin] = max(se, se0);
 			if (bin_cost) bin_cost[bin] = max(se, se0); // how far this bin was walked: the next frame's launch order (lgs_bin.cu)
 		}
-		feed_finish(vfeed, lane);
+		feed_finish(feed, lane);
 	} else {
 		// =============================== worker warp: pixel group `warp`, resumed from kernel B's state ===============
 		GroupWorker w;
@@ -389,19 +388,19 @@ render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 		       n_contrib, fin);
 		unsigned pos = se0;
 		while (w.live) {
-			const unsigned avail = feed_wait(vfeed, pos); // > pos, or pos once the sorter has stopped there
+			const unsigned avail = feed_wait(feed, pos, lane); // > pos, or pos once the sorter has stopped there
 			if (avail <= pos) break;
 			uint2 enext = feed_load_idy(ebin, pos + (unsigned)lane, avail);
 			for (unsigned j0 = pos; j0 < avail && w.live; j0 += 32) {
 				const uint2 e = enext; // (lanes beyond the sorted part hold zeros: empty y range)
 				enext = feed_load_idy(ebin, j0 + 32u + (unsigned)lane, avail);
 				w.scan32(e.x, e.y, j0 + (unsigned)lane);
-				if (lane == 0) vfeed->prog[warp] = min(j0 + 32u, avail);
+				if (lane == 0) feed_st(&feed->prog[warp], min(j0 + 32u, avail));
 			}
 			pos = avail;
 		}
 		if (lane == 0) {
-			vfeed->prog[warp] = 0xffffffffu;
+			feed_st(&feed->prog[warp], 0xffffffffu);
 			if (w.live == 0) atomicAdd(&feed->ndone, 1u);
 		}
 		if (w.live) w.flush(); // the list ended with pairs still queued
@@ -416,7 +415,7 @@ render_fwd_tail_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint32
 	}
 	__syncwarp();
 	if (lane == 0 && atomicAdd(&feed->nfin, 1u) == (unsigned)C::NW - 1u) // last warp out: CTA diagnostics
-		cta_prof[bin] = make_uint4(t0us, (unsigned)(clock64() - clk0), lgs_smid(), vfeed->nchunks);
+		cta_prof[bin] = make_uint4(t0us, (unsigned)(clock64() - clk0), lgs_smid(), feed_ld(&feed->nchunks));
 }
 
 // ---- kernel P: the same pass with evaluate and blend on DIFFERENT warps ---------------------------------------------------

@@ -402,17 +402,49 @@ struct SortFeed { // in shared memory
 	unsigned pad[3];
 	unsigned prog[16]; // per worker: list position it has scanned up to (0xffffffff: all its pixels have terminated)
 };
+// The words of a SortFeed are only touched through these: cta-scope atomics (an OR with 0 reads, an exchange writes),
+// release on the counters that publish data, acquire on the reads that consume them.  (Atomics rather than strong
+// ld / st so that compute-sanitizer's racecheck, which knows nothing of acquire / release on plain accesses, stays clean.)
+__device__ __forceinline__ unsigned feed_ld(unsigned *p)
+{
+	unsigned v;
+	asm volatile("atom.relaxed.cta.shared.or.b32 %0, [%1], 0;" : "=r"(v) : "r"(lgs_smem_addr(p)) : "memory");
+	return v;
+}
+__device__ __forceinline__ unsigned feed_ld_acquire(unsigned *p)
+{
+	unsigned v;
+	asm volatile("atom.acquire.cta.shared.or.b32 %0, [%1], 0;" : "=r"(v) : "r"(lgs_smem_addr(p)) : "memory");
+	return v;
+}
+__device__ __forceinline__ void feed_st(unsigned *p, unsigned v)
+{
+	unsigned old;
+	asm volatile("atom.relaxed.cta.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(lgs_smem_addr(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void feed_st_release(unsigned *p, unsigned v)
+{
+	unsigned old;
+	asm volatile("atom.release.cta.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(lgs_smem_addr(p)), "r"(v) : "memory");
+}
 __device__ __forceinline__ void feed_init(SortFeed *f, unsigned sorted0)
 {
 	f->sorted = sorted0; f->end = 0; f->ndone = 0; f->nfin = 0; f->nchunks = 0;
 	for (int i = 0; i < 16; i++) f->prog[i] = sorted0;
 }
+// sorter: have all `nworkers` workers terminated?  (One lane reads for the warp: the answer steers the warp's control flow.)
+__device__ __forceinline__ bool feed_all_done(SortFeed *f, int nworkers, int lane)
+{
+	unsigned nd = 0;
+	if (lane == 0) nd = feed_ld(&f->ndone);
+	return __shfl_sync(0xffffffffu, nd, 0) >= (unsigned)nworkers;
+}
 // sorter: may the next segment (the list is sorted up to `sorted_to`) be sorted now?  Waits while it is a window ahead.
-__device__ __forceinline__ void feed_wait_window(volatile SortFeed *f, unsigned sorted_to, int nworkers, int lane)
+__device__ __forceinline__ void feed_wait_window(SortFeed *f, unsigned sorted_to, int nworkers, int lane)
 {
 	const long long t0 = clock64();
 	for (;;) {
-		unsigned p = lane < nworkers ? f->prog[lane] : 0xffffffffu;
+		unsigned p = lane < nworkers ? feed_ld(&f->prog[lane]) : 0xffffffffu;
 		p = __reduce_min_sync(0xffffffffu, p);
 		if (p == 0xffffffffu || sorted_to - min(p, sorted_to) < max(FEED_WINDOW, p << 1)) return;
 		__nanosleep(200);
@@ -420,38 +452,38 @@ __device__ __forceinline__ void feed_wait_window(volatile SortFeed *f, unsigned 
 	}
 }
 // sorter: the list is now sorted up to `sorted_to` (all lanes call; their global stores become visible before the counter)
-__device__ __forceinline__ void feed_publish(volatile SortFeed *f, unsigned sorted_to, int lane)
+__device__ __forceinline__ void feed_publish(SortFeed *f, unsigned sorted_to, int lane)
 {
 	__threadfence_block();
 	__syncwarp();
-	if (lane == 0) {
-		__threadfence_block();
-		f->sorted = sorted_to;
-	}
+	if (lane == 0) feed_st_release(&f->sorted, sorted_to);
 }
-__device__ __forceinline__ void feed_finish(volatile SortFeed *f, int lane)
+__device__ __forceinline__ void feed_finish(SortFeed *f, int lane)
 {
 	__syncwarp();
-	if (lane == 0) {
-		__threadfence_block();
-		f->end = 1u;
-	}
+	if (lane == 0) feed_st_release(&f->end, 1u);
 }
 // worker: how far is the list sorted?  Returns a position > pos, or pos itself once the sorter has stopped there.
-__device__ __forceinline__ unsigned feed_wait(volatile SortFeed *f, unsigned pos)
+// Lane 0 polls (one acquire for the warp: 32 lanes polling on their own could each see a different value); the warp
+// barrier + fence behind it order every lane's loads of the entries after that acquire.
+__device__ __forceinline__ unsigned feed_wait(SortFeed *f, unsigned pos, int lane)
 {
-	unsigned a = f->sorted;
-	if (a <= pos) {
-		const long long t0 = clock64();
-		for (;;) {
-			const unsigned e = f->end; // read before `sorted`: once set, the value read next is final
-			a = f->sorted;
-			if (a > pos || e) break;
-			__nanosleep(100);
-			if (clock64() - t0 > 4000000000ll) __trap();
+	unsigned a = 0;
+	if (lane == 0) {
+		a = feed_ld_acquire(&f->sorted);
+		if (a <= pos) {
+			const long long t0 = clock64();
+			for (;;) {
+				const unsigned e = feed_ld_acquire(&f->end); // read before `sorted`: once set, the value read next is final
+				a = feed_ld_acquire(&f->sorted);
+				if (a > pos || e) break;
+				__nanosleep(100);
+				if (clock64() - t0 > 4000000000ll) __trap(); // a protocol error must not hang the GPU
+			}
 		}
 	}
 	a = __shfl_sync(0xffffffffu, a, 0);
+	__syncwarp();
 	__threadfence_block();
 	return a;
 }

@@ -280,7 +280,6 @@ surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 	const unsigned base = binbase[bin], ntotal = binbase[bin + 1] - base;
 	extern __shared__ __align__(16) unsigned char smem[];
 	SortFeed *feed = reinterpret_cast<SortFeed *>(smem + C::O_FEED);
-	volatile SortFeed *vfeed = feed;
 	unsigned char *ss = smem + C::O_SORT;
 	unsigned *sloc = reinterpret_cast<unsigned *>(ss + SortSmem::LOC);
 	for (int i = tid; i < LGS_NB; i += NT) sloc[i] = loc[(size_t)bin * LGS_NB + i];
@@ -298,20 +297,20 @@ surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 		unsigned upto = 0;
 		const unsigned se = run_sorter<false, true>(
 			ss, unsorted + base, entries + base, ntotal, 0, lane,
-			[&](unsigned) { return sort_all || vfeed->ndone < (unsigned)NPG; },
+			[&](unsigned) { return sort_all || !feed_all_done(feed, NPG, lane); },
 			[&]() {
-				if (!sort_all) feed_wait_window(vfeed, upto, NPG, lane);
+				if (!sort_all) feed_wait_window(feed, upto, NPG, lane);
 				return (uint2 *)nullptr;
 			},
 			[&](unsigned pos0, int m) {
 				upto = pos0 + (unsigned)m;
-				feed_publish(vfeed, upto, lane);
+				feed_publish(feed, upto, lane);
 			});
 		if (lane == 0) {
 			ip.sorted_end[bin] = se;
 			if (bin_cost) bin_cost[bin] = se; // how far this bin was walked: the next frame's launch order (lgs_bin.cu)
 		}
-		feed_finish(vfeed, lane);
+		feed_finish(feed, lane);
 	} else {
 		// =============================== worker warp: pixel group `warp` ===============================
 		SurfelWorker w;
@@ -319,19 +318,19 @@ surfel_render_fwd_kernel(FrameGeom g, const float4 *__restrict__ rec, const uint
 		w.init(smem + C::O_WORK + (size_t)warp * SWorkSmem::BYTES, g, RB, bin, warp, lane, beams, rec, ebin);
 		unsigned pos = 0;
 		while (w.live) {
-			const unsigned avail = feed_wait(vfeed, pos); // > pos, or pos once the sorter has stopped there
+			const unsigned avail = feed_wait(feed, pos, lane); // > pos, or pos once the sorter has stopped there
 			if (avail <= pos) break;
 			uint2 enext = feed_load_idy(ebin, pos + (unsigned)lane, avail);
 			for (unsigned j0 = pos; j0 < avail && w.live; j0 += 32) {
 				const uint2 e = enext; // (lanes beyond the sorted part hold zeros: empty y range)
 				enext = feed_load_idy(ebin, j0 + 32u + (unsigned)lane, avail);
 				w.scan32(e.x, e.y, j0 + (unsigned)lane);
-				if (lane == 0) vfeed->prog[warp] = min(j0 + 32u, avail);
+				if (lane == 0) feed_st(&feed->prog[warp], min(j0 + 32u, avail));
 			}
 			pos = avail;
 		}
 		if (lane == 0) {
-			vfeed->prog[warp] = 0xffffffffu;
+			feed_st(&feed->prog[warp], 0xffffffffu);
 			atomicAdd(&feed->ndone, 1u);
 		}
 		if (w.live) w.flush(); // the list ended with pairs still queued
