@@ -16,4 +16,8 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'ren
     -f -o gpurun_out/${TAG}_kernels python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-workloads > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_full.log | cut -c1-200
 echo "== surfel bench (config 5)"; timeout 600 python bench.py --workload surfel 2>gpurun_out/${TAG}_bench_surfel.err | tee gpurun_out/${TAG}_bench_surfel.json | cut -c1-300
+echo "== ncu full, surfel compositing kernels"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"surfel_render_" -s 6 -c 2 -f -o gpurun_out/${TAG}_surfel \
+    python bench.py --workload surfel --steps 1 --warmup 3 --no-e2e --no-cpu --no-workloads > gpurun_out/${TAG}_surfel_ncu.log 2>&1
+tail -2 gpurun_out/${TAG}_surfel_ncu.log | cut -c1-200
 ls -la gpurun_out | grep ${TAG}_
