@@ -361,7 +361,7 @@ int lgs_set_sort_all(int on);
 /*
  * Shape of the forward compositing pass (all five produce bit-identical images; tests force each of them):
  *   -1 automatic (default): one pipelined launch; two-row worker warps, switching to one-row workers while the previous
- *      frames on the device had pixel groups walking 100 or more chunks of 32 pairs by themselves (rays that never saturate)
+ *      frames on the device had pixel groups walking 60 or more chunks of 32 pairs by themselves (rays that never saturate)
  *    0 one launch, a worker warp per 2 pixel rows          3 one launch, a worker warp per pixel row
  *    1 three launches (prefix sort, independent pixel-group warps, resumable tail)
  *    2 one launch, evaluate and blend on separate warps coupled by an mbarrier ring

@@ -32,6 +32,7 @@ struct DevState {
 	struct Hwm { int P = -1, W = 0, H = 0; long long N = 0; } hwm[2]; // [0] 3-D path, [1] surfel path
 	unsigned *walk_stat = nullptr; // device word: longest walk of the last compositing pass (see FrameTotals::prev_max_chunks)
 	int one_row_workers = 0;       // worker shape the automatic mode currently uses on this device
+	int mode_cur = 0, mode_prev = 0; // forward shape of the frame being enqueued / of the frame before it
 	// how far every bin's list was walked in the last frame of this geometry: the launch order of the next one (lgs_bin.cu)
 	struct Cost { uint32_t *dev = nullptr; int nbins = 0, W = 0, H = 0, RB = 0; bool valid = false; } cost[2];
 };
@@ -217,10 +218,15 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 			// Worker shape of the following frames, from the longest walk of the previous frame's compositing pass (it rode in
 			// with the totals): a pixel group that walks hundreds of chunks by itself is the critical path of the whole kernel
 			// (rays that never saturate), and one warp per pixel ROW halves it at ~4 % more work for everybody else.
+			// (w belongs to the frame BEFORE this one, and reads ~15 % higher when that frame ran with one-row workers.  Measured
+			// on cfg3, two-row / one-row frame time: pose 0 (w = 52 / 58) 0.578 / 0.608 ms, pose 1 (63 / 76) 0.705 / 0.659,
+			// pose 2 (85 / 104) 0.723 / 0.663, pose 5 (131 / 156) 0.792 / 0.687.)
 			const unsigned w = ds->pinned->prev_max_chunks;
 			g_last_walk = w;
-			if (w >= 100) ds->one_row_workers = 1;      // cfg3: 52 chunks from the centre of the cloud, 120-140 from shifted poses
-			else if (w > 0 && w < 75) ds->one_row_workers = 0;
+			if (w > 0) {
+				if (ds->mode_prev != 3) { if (w >= 60) ds->one_row_workers = 1; }
+				else if (w < 66) ds->one_row_workers = 0;
+			}
 		}
 		if (N <= cap) {
 			hw.P = g.P; hw.W = g.W; hw.H = g.H;
@@ -291,6 +297,8 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn 
 			int mode = g_fwd_split.load();
 			if (mode < 0) mode = ds->one_row_workers ? 3 : 0;
 			g_last_fwd_mode = mode;
+			ds->mode_prev = ds->mode_cur;
+			ds->mode_cur = mode;
 			lgs_launch_render_fwd(g, gp, ip, entries, scattered, background, beam_inclinations, out_color, out_depth, out_occ,
 					      g_sort_all.load(), mode, ds->walk_stat, ds->cost[0].dev, st);
 		},

@@ -175,6 +175,21 @@ __global__ void peer_publish_kernel(PeerHeader *mine, unsigned step)
 	st_release_sys(&mine->ready, step + 1u);
 }
 
+// One warp waits for every peer's slot before the pull kernel is allowed to start (stream order): a rank that is ahead of
+// the others would otherwise park the pull kernel's 592 CTAs -- half of every SM's registers and thread slots -- on the GPU
+// for as long as the slowest rank needs, next to the forward pass of the following frame that runs on the other stream.
+__global__ void peer_wait_kernel(int nranks, char *const *__restrict__ peers, size_t slot_off, unsigned step, unsigned *__restrict__ status)
+{
+	for (int r = threadIdx.x; r < nranks; r += blockDim.x) {
+		const PeerHeader *h = reinterpret_cast<const PeerHeader *>(peers[r] + slot_off);
+		const long long t0 = clock64();
+		while (ld_acquire_sys(&h->ready) < step + 1u) {
+			if (clock64() - t0 > 20000000000ll) { atomicExch(&status[0], 2u); break; } // ~10 s: a peer died; never hang the GPU
+			__nanosleep(500);
+		}
+	}
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 peer_pull_kernel(int P, int nranks, int my_rank, char *const *__restrict__ peers, size_t slot_off, int cap, unsigned step,
@@ -296,6 +311,7 @@ int lgs_peer_pull(int P, int nranks, int my_rank, void *const *peer_buffers_dev,
 		return LGS_EINVAL;
 	const size_t slot_off = (size_t)(step & 1u) * (((size_t)cap + 1) * 64);
 	const bool vec = (reinterpret_cast<uintptr_t>(dL_drot) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dL_dcolor) & 7u) == 0;
+	peer_wait_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(nranks, (char *const *)peer_buffers_dev, slot_off, step, status_dev);
 	if (vec)
 		peer_pull_kernel<true><<<148 * 4, 256, 0, (cudaStream_t)stream>>>(P, nranks, my_rank, (char *const *)peer_buffers_dev, slot_off, cap,
 										  step, dL_dmean3D, dL_dscale, dL_drot, dL_dopacity, dL_dcolor, status_dev);
