@@ -216,39 +216,62 @@ peer_pull_kernel(int P, int nranks, int my_rank, char *const *__restrict__ peers
 		if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&status[0], 1u);
 		return;
 	}
-	// all peers' rows as ONE index space (prefix over the peers, own rank skipped): every thread has loads from several
-	// peers in flight at once instead of walking the peers one after the other
+	// All peers' rows as ONE index space of 32-row blocks (prefix over the peers, own rank skipped), one block per warp and
+	// trip: the 2 KB of a block cross the link as four fully coalesced 512-byte loads (lane l takes the float4s l, l + 32,
+	// l + 64, l + 96 of the block: always quarter (l & 3) of a row -- means | scales + opacity | rotation | colours), and each
+	// lane adds its own quarter.  (One lane per row read the same bytes as 4 x 32 strided 16-byte requests.)
 	__shared__ unsigned s_start[65];
 	if (threadIdx.x == 0) {
 		unsigned run = 0, mx = 0;
 		for (int k = 0; k < nranks; k++) {
 			s_start[k] = run;
-			if (k != my_rank) run += s_rows[k];
+			if (k != my_rank) run += (s_rows[k] + 31u) / 32u;
 			mx = max(mx, s_rows[k]);
 		}
 		s_start[nranks] = run;
 		if (blockIdx.x == 0) atomicMax(&status[1], mx);
 	}
 	__syncthreads();
-	const unsigned total = s_start[nranks];
-	for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+	const unsigned nblocks = s_start[nranks];
+	const int lane = threadIdx.x & 31, part = lane & 3;
+	const unsigned wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (unsigned b = wid; b < nblocks; b += nwarps) {
 		int r = 0;
-		while (t >= s_start[r + 1]) r++; // (s_start[r + 1] == s_start[r] for the own rank: never selected)
-		const float4 *row = reinterpret_cast<const float4 *>(peers[r] + slot_off) + 4 * ((size_t)(t - s_start[r]) + 1);
-		const float4 a = __ldcv(row), b = __ldcv(row + 1), c = __ldcv(row + 2), d = __ldcv(row + 3); // peer memory: never from a stale L1 line
-		const unsigned id = __float_as_uint(a.x);
-		if (id >= (unsigned)P) continue;
-		// several ranks may touch the same Gaussian: reductions in L2 (rows of ONE rank are unique, so contention is at most nranks - 1)
-		atomicAdd(d_means3D + 3 * (size_t)id, a.y); atomicAdd(d_means3D + 3 * (size_t)id + 1, a.z); atomicAdd(d_means3D + 3 * (size_t)id + 2, a.w);
-		atomicAdd(d_scales + 3 * (size_t)id, b.x); atomicAdd(d_scales + 3 * (size_t)id + 1, b.y); atomicAdd(d_scales + 3 * (size_t)id + 2, b.z);
-		atomicAdd(d_opac + id, b.w);
-		if (VEC) { // rotation rows 16-byte aligned, colour rows 8-byte aligned (checked by the host): one vector reduction each
-			asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d_rot + 4 * (size_t)id), "f"(c.x), "f"(c.y), "f"(c.z), "f"(c.w) : "memory");
-			asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d_colors + 2 * (size_t)id), "f"(d.x), "f"(d.y) : "memory");
-		} else {
-			atomicAdd(d_rot + 4 * (size_t)id, c.x); atomicAdd(d_rot + 4 * (size_t)id + 1, c.y);
-			atomicAdd(d_rot + 4 * (size_t)id + 2, c.z); atomicAdd(d_rot + 4 * (size_t)id + 3, c.w);
-			atomicAdd(d_colors + 2 * (size_t)id, d.x); atomicAdd(d_colors + 2 * (size_t)id + 1, d.y);
+		while (b >= s_start[r + 1]) r++; // (s_start[r + 1] == s_start[r] for the own rank: never selected)
+		const unsigned row0 = (b - s_start[r]) * 32u, nq = 4u * min(32u, s_rows[r] - row0); // float4s of this block
+		const float4 *base = reinterpret_cast<const float4 *>(peers[r] + slot_off) + 4 * ((size_t)row0 + 1);
+		float4 v[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const unsigned q = (unsigned)lane + 32u * k;
+			v[k] = q < nq ? __ldcv(base + q) : make_float4(0.f, 0.f, 0.f, 0.f); // peer memory: never from a stale L1 line
+		}
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const unsigned q = (unsigned)lane + 32u * k;
+			const unsigned id = __float_as_uint(__shfl_sync(0xffffffffu, v[k].x, lane & ~3)); // the row's index sits in its first quarter
+			if (q >= nq || id >= (unsigned)P) continue;
+			const float4 x = v[k];
+			// several ranks may touch the same Gaussian: reductions in L2 (rows of ONE rank are unique, so contention is at most nranks - 1)
+			if (part == 0) {
+				atomicAdd(d_means3D + 3 * (size_t)id, x.y); atomicAdd(d_means3D + 3 * (size_t)id + 1, x.z); atomicAdd(d_means3D + 3 * (size_t)id + 2, x.w);
+			} else if (part == 1) {
+				atomicAdd(d_scales + 3 * (size_t)id, x.x); atomicAdd(d_scales + 3 * (size_t)id + 1, x.y); atomicAdd(d_scales + 3 * (size_t)id + 2, x.z);
+				atomicAdd(d_opac + id, x.w);
+			} else if (part == 2) {
+				if (VEC) { // rotation rows 16-byte aligned, colour rows 8-byte aligned (checked by the host): one vector reduction each
+					asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d_rot + 4 * (size_t)id), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+				} else {
+					atomicAdd(d_rot + 4 * (size_t)id, x.x); atomicAdd(d_rot + 4 * (size_t)id + 1, x.y);
+					atomicAdd(d_rot + 4 * (size_t)id + 2, x.z); atomicAdd(d_rot + 4 * (size_t)id + 3, x.w);
+				}
+			} else {
+				if (VEC) {
+					asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(d_colors + 2 * (size_t)id), "f"(x.x), "f"(x.y) : "memory");
+				} else {
+					atomicAdd(d_colors + 2 * (size_t)id, x.x); atomicAdd(d_colors + 2 * (size_t)id + 1, x.y);
+				}
+			}
 		}
 	}
 }
