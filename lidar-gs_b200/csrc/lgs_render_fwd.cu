@@ -4,24 +4,27 @@
 // cub::DeviceRadixSortPairs on tile|depth keys (rasterizer_impl.cu:317-322).  A bin is 16 columns x RB rows of
 // pixels; its list is bucketed by depth (lgs_bin.cu) and sorted LAZILY, front to back, only as far as the bin's
 // rays travel before the reference's T < 1e-4 stop.  No kernel here has a CTA-wide barrier in its loop.  By default the
-// whole pass is ONE launch of kernel C in "full" mode (every bin starts from scratch); with lgs_set_forward_split(1) a
-// fixed prefix is sorted and composited by fully independent warps first (A, B) and C only continues the bins whose
-// rays outlive the prefix.  Measured on cfg3 (B200): one kernel 0.118 ms, split 0.178 ms -- B alone costs as much as
-// the one-kernel pass (both are bound by instruction issue, ~55 M warp instructions), and the few heavy bins C is left
-// with then run by themselves instead of alongside everything else.
+// whole pass is ONE launch of kernel C in "full" mode (every bin starts from scratch; one worker warp per 2 pixel rows, or
+// per row when the frames on the device contain rays that never saturate: lgs_abi.cu).  Two alternatives are kept behind
+// lgs_set_forward_split() and tested bit-identical: mode 1 = a fixed prefix is sorted and composited by fully independent
+// warps first (A, B) and C only continues the bins whose rays outlive the prefix (cfg3: 0.178 ms against 0.12 ms for the
+// one-kernel pass -- B alone costs as much as the whole pass, both are bound by instruction issue, and the few heavy bins
+// C is left with then run by themselves instead of alongside everything else); mode 2 = kernel P below.
 //
-//   A  sort_prefix_kernel      one warp per bin sorts the first ~FWD_PREFIX entries of the list: whole depth buckets,
-//                              grouped into segments that travel to shared memory as one bulk copy (TMA) each, issued
-//                              one segment ahead; counting sort on the quantised depth + rank inside each sub-bucket
+//   A  sort_prefix_kernel      one warp per bin sorts the first ~FWD_PREFIX entries of the list (lgs_sorter.cuh: whole depth
+//                              buckets grouped into segments that travel to shared memory as one bulk copy (TMA) each,
+//                              issued one segment ahead; counting sort on the quantised depth + rank inside each sub-bucket
 //                              on (depth bits, Gaussian idx) -- the tie-break a stable LSD sort over idx-ordered input
-//                              gives; written back in place (the backward pass replays the sorted prefix).
+//                              gives; written out of place into the sorted list the backward pass replays).
 //   B  render_fwd_groups_kernel one warp per (bin, 32-pixel group = 2 rows x 16 columns), independent of every other
 //                              warp, composites the sorted prefix.  Most rays saturate inside it.
-//   C  render_fwd_tail_kernel  one CTA per bin that B left unfinished (rays still alive at the end of the sorted
-//                              prefix): a sorter warp keeps sorting segments and publishes them through a two-slot
-//                              ring guarded by mbarriers (full / empty), one worker warp per pixel group resumes
-//                              from the state B saved.  It stops sorting as soon as every pixel of the bin has
-//                              terminated: buckets behind the stop are never read, sorted or gathered.
+//   C  render_fwd_tail_kernel  one CTA per bin: a sorter warp sorts segment after segment into the bin's sorted list in
+//                              global memory and publishes how far it got (SortFeed, lgs_sorter.cuh); one worker warp
+//                              per pixel group reads the sorted entries at its own pace (in mode 1: resumed from the
+//                              state B saved).  The sorter pauses a window ahead of the slowest live worker and stops as
+//                              soon as every pixel of the bin has terminated: buckets behind the stop are never read,
+//                              sorted or gathered.
+//   P  render_fwd_pipe_kernel  C with evaluate and blend on separate warps, coupled by a ring of shared-memory slots.
 //
 // A worker (B and C share the code: GroupWorker) scans sorted entries (lanes = entries), keeps the (entry, row) PAIRS
 // whose rect covers one of its two rows and whose row still has live pixels, and queues them.  Every 32 queued pairs
