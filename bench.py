@@ -915,10 +915,16 @@ def main():
             per[s] = {"ms_per_step": tot_ms / nstage, "launches_per_step": n / nstage,
                       "gbs": alg[s] / (tot_ms / nstage * 1e-3) / 1e9}
     dom = max((s for s in per if s != "clear"), key=lambda s: per[s]["ms_per_step"])
-    traffic, traffic_src = None, None
+    traffic, traffic_src, issue = None, None, None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         traffic, traffic_src = tj.get(dom), tj.get("_source")
+        wi = tj.get("_warp_instructions", {})
+        if world == 1 and args.pose_rank is None:  # the counts belong to this workload only
+            # what actually bounds these kernels: warp instructions issued per second against 148 SMs x 4 schedulers x 1 per clock
+            mhz = float(clocks["sm_mhz"]) if clocks and clocks.get("sm_mhz") else 1965.0
+            issue = {k: {"warp_instructions": wi[k], "issue_frac": wi[k] / (per[k]["ms_per_step"] / max(per[k]["launches_per_step"], 1) * 1e-3)
+                         / (148 * 4 * mhz * 1e6)} for k in wi if k in per}
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": per[dom]["gbs"], "peak": peak, "unit": "GB/s",
@@ -930,7 +936,7 @@ def main():
                     "entries + records of the list prefixes actually consumed (extra.consumed), a few percent of the lists"}
     frame_bytes = 124.0 * P + 276.0 * V + 164.0 * R + 48.0 * HW  # SURVEY.md §8d full-sort byte model
     extra = {"num_rendered": R, "num_visible": V, "num_instances": Ninst, "consumed": cons,
-             "stages": per, "frame_model_bytes": frame_bytes,
+             "stages": per, "issue": issue, "frame_model_bytes": frame_bytes,
              "frame_model_note": "SURVEY 8d byte model of the reference's full-sort algorithm -- NOT traffic this implementation moves",
              "longest_walk_chunks": int(L.lgs_last_longest_walk()),
              "forward_mode": int(L.lgs_last_forward_mode()),  # 0: worker warp per 2 pixel rows, 3: per row (automatic)
