@@ -67,6 +67,10 @@ def test_host_side_validation_without_device():
     for ok in (0, 1, 2, 4, 8, 16):
         assert L.lgs_set_rows_per_bin(ok) == 0
     L.lgs_set_rows_per_bin(0)
+    assert L.lgs_set_forward_split(4) < 0 and L.lgs_set_forward_split(-2) < 0
+    for ok in (0, 1, 2, 3, -1):
+        assert L.lgs_set_forward_split(ok) == 0
+    assert L.lgs_set_order_history(0) == 0 and L.lgs_set_order_history(1) == 0  # a scheduling hint: on by default
     assert L.lgs_backward_scratch_bytes(1000) >= 1000 * 20 * 4
     assert L.lgs_backward_scratch_bytes(1000) % 256 == 0
     # argument errors are reported before anything touches CUDA
