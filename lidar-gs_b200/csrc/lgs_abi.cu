@@ -35,6 +35,7 @@ struct DevState {
 	int mode_cur = 0, mode_prev = 0; // forward shape of the frame being enqueued / of the frame before it
 	// how far every bin's list was walked in the last frame of this geometry: the launch order of the next one (lgs_bin.cu)
 	struct Cost { uint32_t *dev = nullptr; int nbins = 0, W = 0, H = 0, RB = 0; bool valid = false; } cost[2];
+	uint32_t *cost_w = nullptr; // the array the frame being enqueued writes (nullptr: hint switched off)
 };
 #define LGS_MAX_DEVICES 64
 thread_local DevState g_dev[LGS_MAX_DEVICES];
@@ -168,16 +169,19 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 	if (g_capacity_hint.load() > 0) cap = (size_t)g_capacity_hint.load();
 	else if (hw.P == g.P && hw.W == g.W && hw.H == g.H && hw.N > 0) cap = (size_t)hw.N + (size_t)hw.N / 4 + 4096;
 	else cap = 4 * (size_t)g.P + 4096;
-	// launch-order hint: per-bin walk depth of the previous frame of the same geometry on this device
+	// launch-order hint: per-bin walk depth of the previous frame of the same geometry on this device (nothing is allocated,
+	// written or read while lgs_set_order_history(0) is in force)
 	DevState::Cost &co = ds->cost[path];
-	if (co.nbins != g.nbins || co.W != g.W || co.H != g.H || co.RB != g.RB) {
+	const bool use_history = g_order_history.load() != 0;
+	if (!use_history) co.valid = false;
+	else if (!co.dev || co.nbins != g.nbins || co.W != g.W || co.H != g.H || co.RB != g.RB) {
 		if (co.dev) cudaFree(co.dev);
 		co = DevState::Cost();
 		CK(cudaMalloc(&co.dev, (size_t)g.nbins * sizeof(uint32_t)));
 		CK(cudaMemsetAsync(co.dev, 0, (size_t)g.nbins * sizeof(uint32_t), st));
 		co.nbins = g.nbins; co.W = g.W; co.H = g.H; co.RB = g.RB;
 	}
-	const bool use_history = g_order_history.load() != 0;
+	ds->cost_w = use_history ? co.dev : nullptr; // what this frame's compositing pass writes
 	for (int attempt = 0;; attempt++) {
 		if (cap > 0xfffffff0ull) return fail(LGS_EINVAL, "binning buffer would exceed 2^32 instances");
 		// sorted lists (offset 0: what the backward pass is handed) | lists as scattered | rank stream = 36 B per instance
@@ -231,7 +235,7 @@ int bin_and_render(int path, const FrameGeom &g, const GeomPtrs &gp, lgs_alloc_f
 		if (N <= cap) {
 			hw.P = g.P; hw.W = g.W; hw.H = g.H;
 			hw.N = (long long)N;
-			co.valid = true; // (the compositing pass of this frame is writing it)
+			co.valid = use_history; // (the compositing pass of this frame is writing it)
 			return 0;
 		}
 		if (attempt >= 1) return fail(LGS_ECUDA, "binning buffer overflow after re-sizing (internal error)");
@@ -300,7 +304,7 @@ int lgs_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_alloc_fn 
 			ds->mode_prev = ds->mode_cur;
 			ds->mode_cur = mode;
 			lgs_launch_render_fwd(g, gp, ip, entries, scattered, background, beam_inclinations, out_color, out_depth, out_occ,
-					      g_sort_all.load(), mode, ds->walk_stat, ds->cost[0].dev, st);
+					      g_sort_all.load(), mode, ds->walk_stat, ds->cost_w, st);
 		},
 		&R);
 	if (rc < 0) return rc;
@@ -467,7 +471,7 @@ int lgs_surfel_forward(lgs_alloc_fn geometry_buffer, void *geometry_user, lgs_al
 		},
 		[&](uint4 *entries, uint4 *scattered, DevState *ds) {
 			lgs_launch_surfel_render_fwd(g, gp, ip, entries, scattered, background, beam_inclinations, out_color, out_others,
-						     g_sort_all.load(), ds->cost[1].dev, st);
+						     g_sort_all.load(), ds->cost_w, st);
 		},
 		&R);
 	if (rc < 0) return rc;
